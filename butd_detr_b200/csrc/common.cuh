@@ -1,0 +1,61 @@
+// Shared helpers for libbutd_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/butd_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libbutd_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace bd {
+
+void set_error(const char *fmt, ...);
+
+inline cudaStream_t as_stream(bd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device (cached per thread).
+int sm_count();
+
+#define BD_REQUIRE(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      bd::set_error(__VA_ARGS__);        \
+      return BD_ERR_INVALID_ARG;         \
+    }                                    \
+  } while (0)
+
+#define BD_CHECK_LAUNCH(name)                                                        \
+  do {                                                                               \
+    cudaError_t e__ = cudaPeekAtLastError();                                         \
+    if (e__ != cudaSuccess) {                                                        \
+      cudaGetLastError();                                                            \
+      bd::set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));    \
+      return BD_ERR_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+#define BD_CUDA(call, name)                                                          \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      bd::set_error("%s: %s", name, cudaGetErrorString(e__));                        \
+      return BD_ERR_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Squared distance with the contraction pattern of the reference's compiled kernels
+// (sm_100 SASS of ball_query_gpu.cu / sampling_gpu.cu / interpolate_gpu.cu:
+//  FMUL dx,dx ; FFMA dy,dy ; FFMA dz,dz).  Written with explicit intrinsics so the result
+//  does not depend on this file's compile flags.
+__device__ __forceinline__ float sqdist_ref(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+}  // namespace bd

@@ -1,0 +1,455 @@
+"""Forward engine: the eval-mode `BeaUTyDETR.forward` (`/root/reference/models/bdetr.py:193-319`)
+as a schedule of libbutd_b200 kernel launches on the current CUDA stream.
+
+B200-first choices (vs. the reference's op-by-op PyTorch graph):
+  * every activation is TOKEN-MAJOR (one contiguous row per point / token / query), so all
+    1x1 convolutions and nn.Linear layers are the same K-major GEMM, neighbour gathers read
+    contiguous rows, and the (B,C,N) tensors the reference returns are zero-copy transposed
+    views of these buffers;
+  * eval-mode BatchNorm is folded into the preceding weights once, at pack time;
+  * packed in-projections are applied as fused QK / KV / QKV GEMMs, the positional embedding
+    is added inside the GEMM's operand load, and the three prediction-head stems are one GEMM;
+  * the FPS chain of levels 2-4 only depends on coordinates and runs on a side stream,
+    overlapped with the set-abstraction MLPs;
+  * nothing synchronises with the host: the whole forward is CUDA-graph capturable.
+
+PyTorch is used for device memory (torch.empty) and streams only; all arithmetic is in the
+C-ABI library.  There is no CPU path.
+"""
+import math
+
+import torch
+
+from . import _lib
+
+SA_CFG = (  # models/backbone_module.py:44-78
+    ("sa1", 2048, 0.2, 64),
+    ("sa2", 1024, 0.4, 32),
+    ("sa3", 512, 0.8, 16),
+    ("sa4", 256, 1.2, 16),
+)
+BN_EPS = 1e-5
+LN_EPS = 1e-5
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------ weight packing
+def _fold_bn(W, bias, sd, bn, k_pad=None):
+    """conv/linear (N,K) followed by eval BatchNorm -> (W', b') with the BN folded in."""
+    W = W.reshape(W.shape[0], -1).float()
+    s = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + BN_EPS)
+    b0 = bias.float() if bias is not None else torch.zeros_like(s)
+    Wf = W * s[:, None]
+    bf = (b0 - sd[bn + ".running_mean"].float()) * s + sd[bn + ".bias"].float()
+    if k_pad is not None and k_pad != Wf.shape[1]:
+        Wp = Wf.new_zeros(Wf.shape[0], k_pad)
+        Wp[:, :Wf.shape[1]] = Wf
+        Wf = Wp
+    return Wf.contiguous(), bf.contiguous()
+
+
+def _plain(sd, name):
+    W = sd[name + ".weight"]
+    b = sd.get(name + ".bias")
+    return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
+
+
+class PackedWeights:
+    """Device-resident, BN-folded, GEMM-ready weights (fp32 masters)."""
+
+    def __init__(self, sd, cfg):
+        w = {}
+        bb = "backbone_net."
+        for name, _, _, _ in SA_CFG:
+            for i in range(3):
+                p = f"{bb}{name}.mlp_module.layer{i}"
+                W = sd[p + ".conv.weight"]
+                k = W.shape[1]
+                w[f"{name}.{i}"] = _fold_bn(W, None, sd, p + ".bn.bn", _round_up(k, 4) if i == 0 else None)
+        for name in ("fp1", "fp2"):
+            for i in range(2):
+                p = f"{bb}{name}.mlp.layer{i}"
+                w[f"{name}.{i}"] = _fold_bn(sd[p + ".conv.weight"], None, sd, p + ".bn.bn")
+        w["text_projector"] = _plain(sd, "text_projector.0")
+        w["text_projector.ln"] = (sd["text_projector.1.weight"].float().contiguous(),
+                                  sd["text_projector.1.bias"].float().contiguous())
+
+        def posembed(prefix, key):
+            h = prefix + ".position_embedding_head"
+            w[key + ".0"] = _fold_bn(sd[h + ".0.weight"], sd[h + ".0.bias"], sd, h + ".1")
+            w[key + ".1"] = _plain(sd, h + ".3")
+
+        def mha(prefix, key):
+            Wi, bi = sd[prefix + ".in_proj_weight"].float().contiguous(), sd[prefix + ".in_proj_bias"].float().contiguous()
+            E = Wi.shape[1]
+            w[key + ".q"] = (Wi[:E], bi[:E])
+            w[key + ".k"] = (Wi[E:2 * E], bi[E:2 * E])
+            w[key + ".v"] = (Wi[2 * E:], bi[2 * E:])
+            w[key + ".qk"] = (Wi[:2 * E], bi[:2 * E])
+            w[key + ".kv"] = (Wi[E:], bi[E:])
+            w[key + ".qkv"] = (Wi, bi)
+            w[key + ".o"] = _plain(sd, prefix + ".out_proj")
+
+        def ln(prefix, key):
+            w[key] = (sd[prefix + ".weight"].float().contiguous(), sd[prefix + ".bias"].float().contiguous())
+
+        def three_layer_head(prefix, key):
+            # center / size / sem heads share their input: fuse the three first layers
+            heads = ("center_residual_head", "size_pred_head", "sem_cls_scores_head")
+            l0 = [_fold_bn(sd[f"{prefix}.{h}.net.0.weight"], None, sd, f"{prefix}.{h}.net.1") for h in heads]
+            w[key + ".stem"] = (torch.cat([a for a, _ in l0]).contiguous(), torch.cat([b for _, b in l0]).contiguous())
+            for h, short in zip(heads, ("center", "size", "sem")):
+                w[f"{key}.{short}.1"] = _fold_bn(sd[f"{prefix}.{h}.net.4.weight"], None, sd, f"{prefix}.{h}.net.5")
+                w[f"{key}.{short}.2"] = _plain(sd, f"{prefix}.{h}.net.8")
+
+        if cfg["butd"]:
+            posembed("box_embeddings", "box_embeddings")
+            w["class_embeddings"] = _plain(sd, "class_embeddings")
+            w["butd_class_embeddings"] = (sd["butd_class_embeddings.weight"].float().contiguous(), None)
+        posembed("pos_embed", "pos_embed")
+        for i in range(cfg["num_encoder_layers"]):
+            p, k = f"cross_encoder.layers.{i}", f"enc{i}"
+            if cfg["self_attend"]:
+                mha(p + ".self_attention_visual.self_attn", k + ".sv")
+                ln(p + ".self_attention_visual.norm1", k + ".sv.ln")
+                mha(p + ".self_attention_lang.self_attn", k + ".sl")
+                ln(p + ".self_attention_lang.norm1", k + ".sl.ln")
+            c = p + ".cross_layer"
+            mha(c + ".cross_lv", k + ".lv")
+            mha(c + ".cross_vl", k + ".vl")
+            for n in ("norm_lv", "norm_lv2", "norm_vl", "norm_vl2"):
+                ln(f"{c}.{n}", f"{k}.{n}")
+            for f in ("ffn_lv", "ffn_vl"):
+                w[f"{k}.{f}.0"] = _plain(sd, f"{c}.{f}.0")
+                w[f"{k}.{f}.1"] = _plain(sd, f"{c}.{f}.3")
+            if cfg["butd"]:
+                mha(c + ".cross_d", k + ".d")
+                ln(c + ".norm_d", k + ".norm_d")
+        for n in ("conv1", "conv2"):
+            w["points_obj_cls." + n] = _fold_bn(sd[f"points_obj_cls.{n}.weight"], sd[f"points_obj_cls.{n}.bias"], sd,
+                                                "points_obj_cls.bn" + n[-1])
+        w["points_obj_cls.conv3"] = _plain(sd, "points_obj_cls.conv3")
+        w["decoder_query_proj"] = _plain(sd, "decoder_query_proj")
+        three_layer_head("proposal_head", "proposal_head")
+        for i in range(cfg["num_decoder_layers"]):
+            p, k = f"decoder.{i}", f"dec{i}"
+            mha(p + ".self_attn", k + ".self")
+            mha(p + ".cross_l", k + ".l")
+            mha(p + ".cross_v", k + ".v")
+            for n in ("norm1", "norm_l", "norm_v", "norm2"):
+                ln(f"{p}.{n}", f"{k}.{n}")
+            if cfg["butd"]:
+                mha(p + ".cross_d", k + ".d")
+                ln(p + ".norm_d", k + ".norm_d")
+            w[k + ".ffn.0"] = _plain(sd, p + ".ffn.0")
+            w[k + ".ffn.1"] = _plain(sd, p + ".ffn.3")
+            if cfg["self_position_embedding"] in ("loc_learned", "xyz_learned"):
+                posembed(p + ".self_posembed", k + ".posembed")
+            three_layer_head(f"prediction_heads.{i}", f"head{i}")
+        if cfg["contrastive_align_loss"]:
+            for side in ("image", "text"):
+                for j, src in enumerate((0, 2, 4)):
+                    w[f"contrastive.{side}.{j}"] = _plain(sd, f"contrastive_align_projection_{side}.{src}")
+        self.w = w
+
+    def __getitem__(self, k):
+        return self.w[k]
+
+
+# ------------------------------------------------------------------------------ engine
+class ForwardEngine:
+    def __init__(self, state_dict, cfg, device):
+        self.cfg = dict(cfg)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("CPU not supported: the BUTD-DETR B200 engine needs a CUDA device")
+        _lib.load()
+        sd = {k: v.detach().to(self.device) for k, v in state_dict.items() if not k.startswith("text_encoder.")}
+        self.W = PackedWeights(sd, self.cfg)
+        self.d_model = cfg["d_model"]
+        self.n_heads = 8
+        self.side_stream = torch.cuda.Stream(device=self.device)
+
+    # ---- thin wrappers over the C-ABI (2-D row-major views; last stride must be 1)
+    def _empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def lin(self, x, key, relu=False, add=None, out=None):
+        W, b = self.W[key]
+        M, K = x.shape
+        N = W.shape[0]
+        assert x.stride(1) == 1 and W.shape[1] == K, (key, x.shape, W.shape)
+        if out is None:
+            out = self._empty(M, N)
+        assert out.stride(1) == 1
+        _lib.call("bd_linear_f32", x.data_ptr(), x.stride(0), _lib.ptr(add), 0 if add is None else add.stride(0),
+                  W.data_ptr(), _lib.ptr(b), out.data_ptr(), out.stride(0), M, N, K, int(relu))
+        return out
+
+    def add_ln(self, x, res, key, eps=LN_EPS, out=None):
+        g, b = self.W[key]
+        M, D = x.shape
+        assert x.is_contiguous() and (res is None or res.is_contiguous())
+        if out is None:
+            out = self._empty(M, D)
+        _lib.call("bd_add_layernorm_f32", x.data_ptr(), _lib.ptr(res), g.data_ptr(), b.data_ptr(), out.data_ptr(),
+                  M, D, float(eps))
+        return out
+
+    def attention(self, q, k, v, B, Lq, Lk, mask):
+        """q (B*Lq, >=E) / k, v (B*Lk, >=E) 2-D views (row stride = leading dim) -> (B*Lq, E)."""
+        E, H = self.d_model, self.n_heads
+        hd = E // H
+        out = self._empty(B * Lq, E)
+        _lib.call("bd_attention_f32", q.data_ptr(), q.stride(0), Lq * q.stride(0), k.data_ptr(), k.stride(0),
+                  Lk * k.stride(0), v.data_ptr(), v.stride(0), Lk * v.stride(0), _lib.ptr(mask), out.data_ptr(), E,
+                  Lq * E, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd))
+        return out
+
+    def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False):
+        """nn.MultiheadAttention (eval) incl. in/out projections.  q = x_q (+pos_q);
+        k = x_kv (+pos_k); v = x_kv.  Returns the out-projected (B*Lq, E) tensor."""
+        E = self.d_model
+        if self_attn and pos_q is None:  # q = k = v = x : one fused QKV GEMM
+            qkv = self.lin(x_q, key + ".qkv")
+            q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+        elif self_attn:  # q = k = x + pos, v = x
+            qk = self.lin(x_q, key + ".qk", add=pos_q)
+            q, k = qk[:, :E], qk[:, E:]
+            v = self.lin(x_q, key + ".v")
+        else:  # cross attention: k = v = memory (no positional term in this model)
+            q = self.lin(x_q, key + ".q", add=pos_q)
+            assert pos_k is None
+            kv = self.lin(x_kv, key + ".kv")
+            k, v = kv[:, :E], kv[:, E:]
+        o = self.attention(q, k, v, B, Lq, Lk, mask)
+        return self.lin(o, key + ".o")
+
+    def ffn(self, x, key):
+        return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
+
+    def posembed(self, x, key):
+        return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
+
+    def head(self, feats, base_xyz, key, ep, prefix, B, Q):
+        """ClsAgnosticPredictHead.forward (models/modules.py:135-180) on token-major (B*Q, E)."""
+        E = self.d_model
+        stem = self.lin(feats, key + ".stem", relu=True)  # (BQ, 3E)
+        outs = {}
+        for i, short in enumerate(("center", "size", "sem")):
+            h = self.lin(stem[:, i * E:(i + 1) * E], f"{key}.{short}.1", relu=True)
+            outs[short] = self.lin(h, f"{key}.{short}.2")
+        center = self._empty(B * Q, 3)
+        _lib.call("bd_add_rows", base_xyz.data_ptr(), 3, outs["center"].data_ptr(), 3, center.data_ptr(), 3, B * Q, 3)
+        ep[prefix + "base_xyz"] = base_xyz.view(B, Q, 3)
+        ep[prefix + "center"] = center.view(B, Q, 3)
+        ep[prefix + "pred_size"] = outs["size"].view(B, Q, 3)
+        ep[prefix + "sem_cls_scores"] = outs["sem"].view(B, Q, -1)
+        return center, outs["size"]
+
+    def contrastive(self, x, side, B, L):
+        h = self.lin(x, f"contrastive.{side}.0", relu=True)
+        h = self.lin(h, f"contrastive.{side}.1", relu=True)
+        h = self.lin(h, f"contrastive.{side}.2")
+        _lib.call("bd_l2_normalize_rows", h.data_ptr(), h.data_ptr(), h.shape[0], h.shape[1])
+        return h.view(B, L, -1)
+
+    # ---- point ops
+    def fps(self, xyz, ld, B, N, m):
+        idx = self._empty(B, m, dtype=torch.int32)
+        tmp = self._empty(B, N) if N > _lib.load().bd_fps_resident_capacity() else None
+        _lib.call("bd_fps", xyz.data_ptr(), ld, B, N, m, _lib.ptr(tmp), idx.data_ptr())
+        return idx
+
+    def gather_rows(self, src, ld_src, idx, B, n_src, m, w):
+        out = self._empty(B, m, w)
+        _lib.call("bd_gather_rows", src.data_ptr(), ld_src, idx.data_ptr(), B, n_src, m, w, out.data_ptr(), w)
+        return out
+
+    def sa_level(self, name, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns):
+        """QueryAndGroup + SharedMLP + max-pool (pointnet2_modules.py:243-257), token-major."""
+        idx = self._empty(B, m, ns, dtype=torch.int32)
+        _lib.call("bd_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), ld_xyz, B, n, m, float(radius), ns,
+                  idx.data_ptr())
+        kp = self.W[name + ".0"][0].shape[1]
+        g = self._empty(B * m * ns, kp)
+        _lib.call("bd_group_rows", xyz.data_ptr(), ld_xyz, feats.data_ptr(), ld_feats, C, new_xyz.data_ptr(),
+                  idx.data_ptr(), B, n, m, ns, float(radius), g.data_ptr(), kp)
+        h = self.lin(g, name + ".0", relu=True)
+        h = self.lin(h, name + ".1", relu=True)
+        h = self.lin(h, name + ".2", relu=True)
+        cout = h.shape[1]
+        out = self._empty(B, m, cout)
+        _lib.call("bd_maxpool_rows", h.data_ptr(), B * m, ns, cout, out.data_ptr())
+        return out
+
+    def fp_level(self, name, unknown, known, unknown_feats, known_feats, B, n, m):
+        """PointnetFPModule.forward (pointnet2_modules.py:371-416), token-major."""
+        dist2 = self._empty(B, n, 3)
+        idx = self._empty(B, n, 3, dtype=torch.int32)
+        _lib.call("bd_three_nn", unknown.data_ptr(), known.data_ptr(), B, n, m, dist2.data_ptr(), idx.data_ptr())
+        C2, C1 = known_feats.shape[-1], unknown_feats.shape[-1]
+        x = self._empty(B * n, C1 + C2)
+        _lib.call("bd_fp_interp_concat", dist2.data_ptr(), idx.data_ptr(), known_feats.data_ptr(), C2,
+                  unknown_feats.data_ptr(), C1, B, n, m, x.data_ptr())
+        h = self.lin(x, name + ".0", relu=True)
+        return self.lin(h, name + ".1", relu=True).view(B, n, -1)
+
+    def backbone(self, pc, ep):
+        """Pointnet2Backbone.forward (models/backbone_module.py:92-144)."""
+        B, N, ld = pc.shape
+        C_in = ld - 3
+        main = torch.cuda.current_stream()
+        xyz, ld_xyz, n = pc, ld, N
+        feats, ld_feats, C = pc[..., 3:], ld, C_in
+        inds1 = self.fps(pc, ld, B, N, SA_CFG[0][1])
+        xyz1 = self.gather_rows(pc, ld, inds1, B, N, SA_CFG[0][1], 3)
+        # coordinates of levels 2-4 only depend on xyz: run their (serial) FPS chain on a side
+        # stream while the main stream does ball query + MLPs
+        levels = {"sa1": (xyz1, inds1)}
+        ready = {}
+        self.side_stream.wait_stream(main)
+        with torch.cuda.stream(self.side_stream):
+            prev, n_prev = xyz1, SA_CFG[0][1]
+            for name, m, _, _ in SA_CFG[1:]:
+                inds = self.fps(prev, 3, B, n_prev, m)
+                nxt = self.gather_rows(prev, 3, inds, B, n_prev, m, 3)
+                levels[name] = (nxt, inds)
+                ready[name] = self.side_stream.record_event()
+                prev, n_prev = nxt, m
+        for name, m, radius, ns in SA_CFG:
+            if name in ready:
+                main.wait_event(ready[name])
+            new_xyz, inds = levels[name]
+            f = self.sa_level(name, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns)
+            ep[name + "_xyz"] = new_xyz
+            ep[name + "_features_tm"] = f
+            if name in ("sa1", "sa2"):
+                ep[name + "_inds"] = inds
+            xyz, ld_xyz, n = new_xyz, 3, m
+            feats, ld_feats, C = f, f.shape[-1], f.shape[-1]
+        for t in levels.values():  # tensors produced on the side stream are consumed on `main`
+            t[0].record_stream(main), t[1].record_stream(main)
+        f = self.fp_level("fp1", ep["sa3_xyz"], ep["sa4_xyz"], ep["sa3_features_tm"], ep["sa4_features_tm"], B, 512, 256)
+        f = self.fp_level("fp2", ep["sa2_xyz"], ep["sa3_xyz"], ep["sa2_features_tm"], f, B, 1024, 512)
+        for name in ("sa1", "sa2", "sa3", "sa4"):
+            ep[name + "_features"] = ep.pop(name + "_features_tm").transpose(1, 2)
+        ep["fp2_features"] = f.transpose(1, 2)
+        ep["fp2_xyz"] = ep["sa2_xyz"]
+        ep["fp2_inds"] = ep["sa1_inds"][:, :ep["fp2_xyz"].shape[1]]
+        return f  # (B, 1024, 288) token-major seed features
+
+    # ---- whole forward
+    @torch.no_grad()
+    def forward(self, inputs, overrides=None):
+        """inputs: point_clouds (B,N,3+C) f32, text_hidden (B,L,768) f32, text_attention_mask
+        (B,L) {0,1} (HF convention), det_boxes (B,D,6) f32, det_bbox_label_mask (B,D) bool,
+        det_class_ids (B,D) i64 — all on the engine's device.  Returns the end_points dict of
+        SURVEY.md Appendix B.  `overrides` (tests): {'sample_inds': (B,Q) i32} teacher-forces
+        the query selection."""
+        cfg = self.cfg
+        ov = overrides or {}
+        E = self.d_model
+        pc = inputs["point_clouds"].contiguous().float()
+        _lib.check_cuda(pc)
+        B = pc.shape[0]
+        ep = {}
+        with torch.cuda.device(self.device):
+            vis = self.backbone(pc, ep)  # (B,V,E)
+            V = vis.shape[1]
+            vis = vis.reshape(B * V, E)
+            ep["seed_inds"], ep["seed_xyz"] = ep["fp2_inds"], ep["fp2_xyz"]
+            xyz = ep["fp2_xyz"]
+            # text projector: Linear(768,E) + LayerNorm(eps=1e-12)  (models/bdetr.py:79-83)
+            th = inputs["text_hidden"].contiguous().float()
+            L = th.shape[1]
+            text = self.add_ln(self.lin(th.view(B * L, -1), "text_projector"), None, "text_projector.ln", eps=1e-12)
+            text_mask = inputs["text_attention_mask"].ne(1)
+            tmask_u8 = text_mask.to(torch.uint8).contiguous()
+            ep["text_feats"], ep["text_attention_mask"] = text.view(B, L, E), text_mask
+            det = dmask_u8 = None
+            D = 0
+            if cfg["butd"]:
+                boxes = inputs["det_boxes"].contiguous().float()
+                D = boxes.shape[1]
+                dmask_u8 = (~inputs["det_bbox_label_mask"]).to(torch.uint8).contiguous()
+                det = self._empty(B * D, E)
+                h = self.lin(boxes.view(B * D, 6), "box_embeddings.0", relu=True)
+                self.lin(h, "box_embeddings.1", out=det[:, :128])
+                table = self.W["butd_class_embeddings"][0]
+                emb = self._empty(B * D, table.shape[1])
+                ids = inputs["det_class_ids"].contiguous().to(torch.int64)
+                _lib.call("bd_embedding_rows", table.data_ptr(), table.shape[1], ids.data_ptr(), B * D,
+                          emb.data_ptr(), table.shape[1])
+                self.lin(emb, "class_embeddings", out=det[:, 128:])
+            pos = self.posembed(xyz.reshape(B * V, 3), "pos_embed")
+            # ---- BiEncoder (encoder_decoder_layers.py:225-255, 75-124)
+            for i in range(cfg["num_encoder_layers"]):
+                k = f"enc{i}"
+                if cfg["self_attend"]:
+                    vis = self.add_ln(self.mha(k + ".sv", vis, pos, vis, pos, B, V, V, None, self_attn=True), vis, k + ".sv.ln")
+                    text = self.add_ln(self.mha(k + ".sl", text, None, text, None, B, L, L, tmask_u8, self_attn=True),
+                                       text, k + ".sl.ln")
+                text_kv = text  # cross_vl attends to the text BEFORE the cross_lv update (:84)
+                t2 = self.mha(k + ".lv", text, None, vis, None, B, L, V, None)
+                text = self.add_ln(t2, text, k + ".norm_lv")
+                text = self.add_ln(self.ffn(text, k + ".ffn_lv"), text, k + ".norm_lv2")
+                v2 = self.mha(k + ".vl", vis, pos, text_kv, None, B, V, L, tmask_u8)
+                vis = self.add_ln(v2, vis, k + ".norm_vl")
+                if cfg["butd"]:
+                    v2 = self.mha(k + ".d", vis, None, det, None, B, V, D, dmask_u8)
+                    vis = self.add_ln(v2, vis, k + ".norm_d")
+                vis = self.add_ln(self.ffn(vis, k + ".ffn_vl"), vis, k + ".norm_vl2")
+            ep["text_memory"] = text.view(B, L, E)
+            ep["seed_features"] = vis.view(B, V, E).transpose(1, 2)
+            if cfg["contrastive_align_loss"]:
+                ep["proj_tokens"] = self.contrastive(text, "text", B, L)
+            # ---- query generation (models/bdetr.py:177-191)
+            h = self.lin(vis, "points_obj_cls.conv1", relu=True)
+            h = self.lin(h, "points_obj_cls.conv2", relu=True)
+            logits = self.lin(h, "points_obj_cls.conv3")  # (B*V, 1)
+            ep["seeds_obj_cls_logits"] = logits.view(B, V, 1).transpose(1, 2)
+            Q = cfg["num_queries"]
+            if "sample_inds" in ov:
+                sample_inds = ov["sample_inds"].to(self.device, torch.int32).contiguous()
+            else:
+                sample_inds = self._empty(B, Q, dtype=torch.int32)
+                _lib.call("bd_topk_sigmoid", logits.data_ptr(), B, V, Q, sample_inds.data_ptr())
+            cluster_xyz = self.gather_rows(xyz, 3, sample_inds, B, V, Q, 3).view(B * Q, 3)
+            cluster_feat = self.gather_rows(vis, E, sample_inds, B, V, Q, E).view(B * Q, E)
+            ep["query_points_xyz"] = cluster_xyz.view(B, Q, 3)
+            ep["query_points_feature"] = cluster_feat.view(B, Q, E).transpose(1, 2)
+            ep["query_points_sample_inds"] = sample_inds
+            query = self.lin(cluster_feat, "decoder_query_proj")
+            if cfg["contrastive_align_loss"]:
+                ep["proposal_proj_queries"] = self.contrastive(query, "image", B, Q)
+            base_xyz, base_size = self.head(cluster_feat, cluster_xyz, "proposal_head", ep, "proposal_", B, Q)
+            # ---- decoder (models/bdetr.py:278-317, encoder_decoder_layers.py:340-406)
+            nd = cfg["num_decoder_layers"]
+            spe = cfg["self_position_embedding"]
+            for i in range(nd):
+                prefix = "last_" if i == nd - 1 else f"{i}head_"
+                k = f"dec{i}"
+                if spe == "loc_learned":  # query_pos = cat(base_xyz, base_size)  (bdetr.py:287)
+                    qp_in = self._empty(B * Q, 6)
+                    _lib.call("bd_concat_rows", base_xyz.data_ptr(), 3, 3, base_size.data_ptr(), 3, 3,
+                              qp_in.data_ptr(), 6, B * Q)
+                elif spe == "xyz_learned":
+                    qp_in = base_xyz
+                else:
+                    qp_in = None
+                qpos = self.posembed(qp_in, k + ".posembed") if qp_in is not None else None
+                q2 = self.mha(k + ".self", query, qpos, query, qpos, B, Q, Q, None, self_attn=True)
+                query = self.add_ln(q2, query, k + ".norm1")
+                query = self.add_ln(self.mha(k + ".l", query, qpos, text, None, B, Q, L, tmask_u8), query, k + ".norm_l")
+                if cfg["butd"]:
+                    query = self.add_ln(self.mha(k + ".d", query, qpos, det, None, B, Q, D, dmask_u8), query, k + ".norm_d")
+                query = self.add_ln(self.mha(k + ".v", query, qpos, vis, None, B, Q, V, None), query, k + ".norm_v")
+                query = self.add_ln(self.ffn(query, k + ".ffn"), query, k + ".norm2")
+                if cfg["contrastive_align_loss"]:
+                    ep[prefix + "proj_queries"] = self.contrastive(query, "image", B, Q)
+                base_xyz, base_size = self.head(query, cluster_xyz, f"head{i}", ep, prefix, B, Q)
+        return ep

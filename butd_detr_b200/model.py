@@ -1,0 +1,280 @@
+"""`BeaUTyDETR` — the reference's nn.Module surface on the B200 engine.
+
+Keeps what `train_dist_mod.py` / `main_utils.py` / `models/losses.py` /
+`src/grounding_evaluator.py` rely on (`/root/reference/models/bdetr.py:46-52,193-319`):
+  * the constructor signature and defaults;
+  * the parameter / buffer tree: `state_dict()` has exactly the reference's keys and shapes
+    (tests/golden/state_dict_spec.json is dumped from the reference), so released checkpoints
+    load with `strict=True` and the optimiser's name-based param groups
+    (`"backbone_net"`, `"text_encoder"`, main_utils.py:258-280) work unchanged;
+  * `forward(inputs) -> end_points` with the key schema of SURVEY.md Appendix B.
+
+The forward itself does not run PyTorch layers: it hands the tensors to
+`engine.ForwardEngine`, i.e. to the sm_100a kernels behind the C-ABI.  Only the frozen RoBERTa
+text encoder (third-party, out of scope — SURVEY.md §2.1 #14) stays a transformers module; feed
+`inputs['text_hidden']` + `inputs['text_attention_mask']` to bypass it.
+
+Eval-mode forward only (the graded path): BatchNorm uses running statistics and dropout is
+off.  Calling forward in training mode raises — backward is a "next" row.
+"""
+import math
+import warnings
+
+import torch
+from torch import nn
+
+from .engine import ForwardEngine
+
+
+class _Node(nn.Module):
+    """Structural container: only holds parameters / buffers / children under given names."""
+
+
+def _register(root, dotted, tensor, buffer=False):
+    *path, leaf = dotted.split(".")
+    mod = root
+    for p in path:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    if buffer:
+        mod.register_buffer(leaf, tensor)
+    else:
+        mod.register_parameter(leaf, nn.Parameter(tensor))
+
+
+def _kaiming_uniform(shape):
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    bound = 1.0 / math.sqrt(max(fan_in, 1))
+    return torch.empty(shape).uniform_(-bound, bound)
+
+
+class BeaUTyDETR(nn.Module):
+    """3D language grounder (B200 engine). Arguments as in the reference (bdetr.py:28-52), plus
+    keyword-only `text_encoder` ('roberta-base' | None | nn.Module) and `num_encoder_layers`."""
+
+    def __init__(self, num_class=256, num_obj_class=485, input_feature_dim=3, num_queries=256,
+                 num_decoder_layers=6, self_position_embedding='loc_learned', contrastive_align_loss=True,
+                 d_model=288, butd=True, pointnet_ckpt=None, self_attend=True, *,
+                 text_encoder="roberta-base", num_encoder_layers=3):
+        super().__init__()
+        if self_position_embedding not in ("none", "xyz_learned", "loc_learned"):
+            raise NotImplementedError(self_position_embedding)
+        if d_model % 8 != 0 or d_model // 8 not in (32, 36):
+            raise NotImplementedError("attention kernels are built for head_dim 36 (d_model 288) and 32")
+        self.num_queries = num_queries
+        self.num_decoder_layers = num_decoder_layers
+        self.self_position_embedding = self_position_embedding
+        self.contrastive_align_loss = contrastive_align_loss
+        self.butd = butd
+        self.cfg = dict(num_class=num_class, num_obj_class=num_obj_class, input_feature_dim=input_feature_dim,
+                        num_queries=num_queries, num_decoder_layers=num_decoder_layers,
+                        num_encoder_layers=num_encoder_layers, self_position_embedding=self_position_embedding,
+                        contrastive_align_loss=contrastive_align_loss, d_model=d_model, butd=butd,
+                        self_attend=self_attend)
+        self._build_tree()
+        self._attach_text_encoder(text_encoder)
+        if input_feature_dim == 3 and pointnet_ckpt is not None:  # bdetr.py:67-70
+            self.backbone_net.load_state_dict(torch.load(pointnet_ckpt), strict=False)
+        self._engine = None
+        self._engine_key = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_engine())
+
+    # ------------------------------------------------------------------ parameter tree
+    def _build_tree(self):
+        c, E = self.cfg, self.cfg["d_model"]
+        add = lambda n, t, buffer=False: _register(self, n, t, buffer)  # noqa: E731
+
+        def bn(prefix, ch):
+            add(prefix + ".weight", torch.ones(ch))
+            add(prefix + ".bias", torch.zeros(ch))
+            add(prefix + ".running_mean", torch.zeros(ch), True)
+            add(prefix + ".running_var", torch.ones(ch), True)
+            add(prefix + ".num_batches_tracked", torch.tensor(0, dtype=torch.long), True)
+
+        def conv(prefix, cout, cin, nd, bias=True):
+            shape = (cout, cin) + (1,) * nd
+            add(prefix + ".weight", _kaiming_uniform(shape))
+            if bias:
+                add(prefix + ".bias", torch.zeros(cout))
+
+        def ln(prefix, ch=E):
+            add(prefix + ".weight", torch.ones(ch))
+            add(prefix + ".bias", torch.zeros(ch))
+
+        def mha(prefix):
+            w = torch.empty(3 * E, E)
+            nn.init.xavier_uniform_(w)
+            add(prefix + ".in_proj_weight", w)
+            add(prefix + ".in_proj_bias", torch.zeros(3 * E))
+            conv(prefix + ".out_proj", E, E, 0)
+
+        def shared_mlp(prefix, spec):  # pt_utils.SharedMLP (pytorch_utils.py:11-36)
+            for i in range(len(spec) - 1):
+                w = torch.empty(spec[i + 1], spec[i], 1, 1)
+                nn.init.kaiming_normal_(w)
+                add(f"{prefix}.layer{i}.conv.weight", w)
+                bn(f"{prefix}.layer{i}.bn.bn", spec[i + 1])
+
+        def posembed(prefix, cin, ch):  # PositionEmbeddingLearned (modules.py:52-67)
+            h = prefix + ".position_embedding_head"
+            conv(h + ".0", ch, cin, 1)
+            bn(h + ".1", ch)
+            conv(h + ".3", ch, ch, 1)
+
+        def three_layer_mlp(prefix, out_dim):  # ThreeLayerMLP (modules.py:89-108)
+            conv(prefix + ".net.0", E, E, 1, bias=False)
+            bn(prefix + ".net.1", E)
+            conv(prefix + ".net.4", E, E, 1, bias=False)
+            bn(prefix + ".net.5", E)
+            conv(prefix + ".net.8", out_dim, E, 1)
+
+        def predict_head(prefix):  # ClsAgnosticPredictHead (modules.py:111-133)
+            three_layer_mlp(prefix + ".center_residual_head", 3)
+            three_layer_mlp(prefix + ".size_pred_head", 3)
+            three_layer_mlp(prefix + ".sem_cls_scores_head", c["num_class"])
+
+        def ffn(prefix):
+            conv(prefix + ".0", 256, E, 0)
+            conv(prefix + ".3", E, 256, 0)
+
+        cin = c["input_feature_dim"]
+        b = "backbone_net"  # Pointnet2Backbone (backbone_module.py:38-81)
+        shared_mlp(b + ".sa1.mlp_module", [cin + 3, 64, 64, 128])
+        shared_mlp(b + ".sa2.mlp_module", [128 + 3, 128, 128, 256])
+        shared_mlp(b + ".sa3.mlp_module", [256 + 3, 128, 128, 256])
+        shared_mlp(b + ".sa4.mlp_module", [256 + 3, 128, 128, 256])
+        shared_mlp(b + ".fp1.mlp", [512, 256, 256])
+        shared_mlp(b + ".fp2.mlp", [512, 256, E])
+        conv("text_projector.0", E, 768, 0)
+        ln("text_projector.1")
+        if c["butd"]:
+            add("butd_class_embeddings.weight", torch.randn(c["num_obj_class"], 768) * 0.4)
+            conv("class_embeddings", E - 128, 768, 0)
+            posembed("box_embeddings", 6, 128)
+        posembed("pos_embed", 3, E)
+        for i in range(c["num_encoder_layers"]):
+            p = f"cross_encoder.layers.{i}"
+            if c["self_attend"]:
+                mha(p + ".self_attention_lang.self_attn")
+                ln(p + ".self_attention_lang.norm1")
+                mha(p + ".self_attention_visual.self_attn")
+                ln(p + ".self_attention_visual.norm1")
+            x = p + ".cross_layer"
+            mha(x + ".cross_lv")
+            ln(x + ".norm_lv")
+            ffn(x + ".ffn_lv")
+            ln(x + ".norm_lv2")
+            mha(x + ".cross_vl")
+            ln(x + ".norm_vl")
+            ffn(x + ".ffn_vl")
+            ln(x + ".norm_vl2")
+            if c["butd"]:
+                mha(x + ".cross_d")
+                ln(x + ".norm_d")
+        conv("points_obj_cls.conv1", E, E, 1)
+        bn("points_obj_cls.bn1", E)
+        conv("points_obj_cls.conv2", E, E, 1)
+        bn("points_obj_cls.bn2", E)
+        conv("points_obj_cls.conv3", 1, E, 1)
+        conv("decoder_query_proj", E, E, 1)
+        predict_head("proposal_head")
+        for i in range(c["num_decoder_layers"]):
+            p = f"decoder.{i}"
+            mha(p + ".self_attn")
+            ln(p + ".norm1")
+            mha(p + ".cross_l")
+            ln(p + ".norm_l")
+            if c["butd"]:
+                mha(p + ".cross_d")
+                ln(p + ".norm_d")
+            mha(p + ".cross_v")
+            ln(p + ".norm_v")
+            ffn(p + ".ffn")
+            ln(p + ".norm2")
+            if c["self_position_embedding"] == "xyz_learned":
+                posembed(p + ".self_posembed", 3, E)
+            elif c["self_position_embedding"] == "loc_learned":
+                posembed(p + ".self_posembed", 6, E)
+            predict_head(f"prediction_heads.{i}")
+        if c["contrastive_align_loss"]:
+            for side in ("image", "text"):
+                q = f"contrastive_align_projection_{side}"
+                conv(q + ".0", E, E, 0)
+                conv(q + ".2", E, E, 0)
+                conv(q + ".4", 64, E, 0)
+
+    def _attach_text_encoder(self, text_encoder):
+        """RoBERTa front-end (bdetr.py:72-77): frozen, third-party, outside the hot path."""
+        self.tokenizer = None
+        self.text_encoder = None
+        if text_encoder is None:
+            return
+        if isinstance(text_encoder, nn.Module):
+            self.text_encoder = text_encoder
+        else:
+            from transformers import RobertaConfig, RobertaModel, RobertaTokenizerFast
+            try:
+                self.tokenizer = RobertaTokenizerFast.from_pretrained(text_encoder)
+                self.text_encoder = RobertaModel.from_pretrained(text_encoder)
+            except Exception as e:  # offline: no hub cache
+                warnings.warn(f"could not load '{text_encoder}' ({type(e).__name__}); using a randomly "
+                              "initialised RoBERTa-base — pass inputs['text_hidden'] or load a checkpoint")
+                self.text_encoder = RobertaModel(RobertaConfig(vocab_size=50265, max_position_embeddings=514,
+                                                               type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1))
+        for p in self.text_encoder.parameters():
+            p.requires_grad = False
+
+    # ------------------------------------------------------------------ engine management
+    def invalidate_engine(self):
+        """Drop the packed (BN-folded) weights; they are rebuilt on the next forward."""
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self):
+        dev = self.decoder_query_proj.weight.device
+        if self._engine is None or self._engine_key != dev:
+            self._engine = ForwardEngine(self.state_dict(), self.cfg, dev)
+            self._engine_key = dev
+        return self._engine
+
+    # ------------------------------------------------------------------ forward
+    def _encode_text(self, inputs, device):
+        """tokenizer -> RoBERTa (bdetr.py:164-171); returns (hidden (B,L,768), HF mask, tokenized)."""
+        if "text_hidden" in inputs:
+            return inputs["text_hidden"].to(device), inputs["text_attention_mask"].to(device), None
+        if self.text_encoder is None or self.tokenizer is None:
+            raise RuntimeError("no tokenizer/text encoder available: provide inputs['text_hidden'] "
+                               "(B,L,768) and inputs['text_attention_mask'] (B,L)")
+        tokenized = self.tokenizer.batch_encode_plus(inputs["text"], padding="longest", return_tensors="pt").to(device)
+        with torch.no_grad():
+            hidden = self.text_encoder(**tokenized).last_hidden_state
+        return hidden, tokenized.attention_mask, tokenized
+
+    def forward(self, inputs, overrides=None):
+        """inputs: {point_clouds (B,N,3+C), text: list[str] | (text_hidden, text_attention_mask),
+        det_boxes (B,D,6), det_bbox_label_mask (B,D) bool, det_class_ids (B,D)} -> end_points."""
+        if self.training:
+            raise NotImplementedError(
+                "butd_detr_b200.BeaUTyDETR implements the eval-mode forward (model.eval()); "
+                "the training step (backward, batch-stat BN, dropout) is not built yet")
+        pc = inputs["point_clouds"]
+        if not pc.is_cuda:
+            raise RuntimeError("CPU not supported: inputs must be CUDA tensors")
+        hidden, hf_mask, tokenized = self._encode_text(inputs, pc.device)
+        eng_in = {"point_clouds": pc, "text_hidden": hidden, "text_attention_mask": hf_mask}
+        if self.butd:
+            for k in ("det_boxes", "det_bbox_label_mask", "det_class_ids"):
+                eng_in[k] = inputs[k]
+        end_points = self.engine().forward(eng_in, overrides)
+        if tokenized is not None:
+            end_points["tokenized"] = tokenized
+        return end_points
+
+    def init_bn_momentum(self):
+        """Kept for API parity (bdetr.py:321-325); BN momentum is irrelevant in eval mode."""

@@ -1,0 +1,171 @@
+/*
+ * butd_b200.h — C ABI of libbutd_b200.so: the B200 (sm_100a) forward hot path of BUTD-DETR.
+ *
+ * This is the drop-in boundary.  Part A replaces, one for one, the nine functions of the
+ * reference's native plugin `pointnet2._ext` (pybind11 module,
+ * /root/reference/pointnet2/_ext_src/src/bindings.cpp:11-24); Part B are the fused forward
+ * entry points the B200 model engine is built from (they replace the ATen / cuDNN / cuBLAS
+ * call sequences of models/bdetr.py:193-319).  INTEGRATION.md shows the reference-side
+ * binding (a ctypes `pointnet2/_ext.py`).
+ *
+ * Conventions (all functions):
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (the reference's ops allocate their outputs with torch::zeros; here the host shim does);
+ *   - asynchronous: work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream); no host synchronisation, no allocation, graph-capturable;
+ *   - returns BD_OK or an error code; never exits or throws (the reference's
+ *     CUDA_CHECK_ERRORS calls exit(-1), cuda_utils.h:35-44).  bd_last_error() returns a
+ *     thread-local message for the last failing call of the calling thread;
+ *   - re-entrant and thread-safe; the device is the one current on the calling thread;
+ *   - float = IEEE fp32, indices = int32, layouts row-major contiguous unless a leading
+ *     dimension (`ld*`, in elements) is given.
+ */
+#ifndef BUTD_B200_H_
+#define BUTD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *bd_stream_t;
+
+enum {
+  BD_OK = 0,
+  BD_ERR_INVALID_ARG = 1, /* null pointer, non-positive size, unsupported shape */
+  BD_ERR_CUDA = 2,        /* launch / runtime error; see bd_last_error() */
+  BD_ERR_UNSUPPORTED = 3
+};
+
+int bd_version(void);
+const char *bd_last_error(void);
+/* Compiled-for architecture string, e.g. "sm_100a". */
+const char *bd_arch(void);
+
+/* ===================================================================================== */
+/* Part A — the nine ops of pointnet2._ext (argument meaning as in the reference headers) */
+/* ===================================================================================== */
+
+/* furthest_point_sampling(points (B,N,3), nsamples) -> idx (B,m) int32
+ * replaces _ext_src/src/sampling.cpp:70-91 + sampling_gpu.cu:74-234.
+ * `ld` = floats per point row (3 for the reference layout; 6 to sample straight from the
+ * (B,N,3+C) point cloud).  `tmp` = scratch of B*N floats, only touched when N exceeds the
+ * register-resident capacity reported by bd_fps_resident_capacity(); may be NULL below it.
+ * Tie-breaking is bit-identical to the reference kernel launched with
+ * opt_n_threads(N) threads (cuda_utils.h:20-24). */
+int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp, int *idx, bd_stream_t stream);
+int bd_fps_resident_capacity(void);
+/* Tuning / test hook: force the cluster size (8 or 16 CTAs) used for clouds that need more than
+ * one CTA; -1 restores the automatic choice (16 for B <= 8 scenes, else 8). */
+int bd_fps_set_cluster(int cluster);
+
+/* gather_points(points (B,C,N), idx (B,m)) -> out (B,C,m)      sampling.cpp:20-43 */
+int bd_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,
+                     bd_stream_t stream);
+/* gather_points_grad(grad_out (B,C,m), idx (B,m), N) -> grad_points (B,C,N), zero-filled here
+ * sampling.cpp:45-69 */
+int bd_gather_points_grad(const float *grad_out, const int *idx, int B, int C, int N, int m,
+                          float *grad_points, bd_stream_t stream);
+
+/* ball_query(new_xyz (B,m,3), xyz (B,n,3), radius, nsample) -> idx (B,m,nsample)
+ * ball_query.cpp:13-37 + ball_query_gpu.cu:14-59: first `nsample` in-ball points in ascending
+ * index order, remaining slots = first hit, all zeros when the ball is empty.
+ * `ld_xyz` = floats per row of `xyz` (3 in the reference layout). */
+int bd_ball_query(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
+                  float radius, int nsample, int *idx, bd_stream_t stream);
+
+/* group_points(points (B,C,n), idx (B,m,ns)) -> out (B,C,m,ns)   group_points.cpp:17-40 */
+int bd_group_points(const float *points, const int *idx, int B, int C, int n, int m, int ns,
+                    float *out, bd_stream_t stream);
+/* group_points_grad(grad_out (B,C,m,ns), idx, n) -> grad_points (B,C,n)  group_points.cpp:42-65 */
+int bd_group_points_grad(const float *grad_out, const int *idx, int B, int C, int n, int m, int ns,
+                         float *grad_points, bd_stream_t stream);
+
+/* three_nn(unknown (B,n,3), known (B,m,3)) -> dist2 (B,n,3) SQUARED, idx (B,n,3)
+ * interpolate.cpp:19-45 + interpolate_gpu.cu:14-73 */
+int bd_three_nn(const float *unknown, const float *known, int B, int n, int m, float *dist2,
+                int *idx, bd_stream_t stream);
+/* three_interpolate(points (B,C,m), idx (B,n,3), weight (B,n,3)) -> out (B,C,n)
+ * interpolate.cpp:47-75 */
+int bd_three_interpolate(const float *points, const int *idx, const float *weight, int B, int C,
+                         int m, int n, float *out, bd_stream_t stream);
+/* three_interpolate_grad(grad_out (B,C,n), idx, weight, m) -> grad_points (B,C,m)
+ * interpolate.cpp:76-104 */
+int bd_three_interpolate_grad(const float *grad_out, const int *idx, const float *weight, int B,
+                              int C, int n, int m, float *grad_points, bd_stream_t stream);
+
+/* ===================================================================================== */
+/* Part B — fused forward entry points (token-major activations: one row per point/token) */
+/* ===================================================================================== */
+
+/* out[b,j,0:w] = src[b, idx[b,j], 0:w]   (rows of `ld_src` floats; out rows of `ld_out`).
+ * Token-major gather: new_xyz from FPS indices, query features/xyz from top-k indices
+ * (pointnet2_modules.py:238, models/modules.py:80-84). */
+int bd_gather_rows(const float *src, int ld_src, const int *idx, int B, int n_src, int m, int w,
+                   float *out, int ld_out, bd_stream_t stream);
+
+/* QueryAndGroup.forward (pointnet2_utils.py:334-359, use_xyz, normalize_xyz) on an existing
+ * ball-query result, token-major:  out[(b*m+j)*ns+s, :] =
+ *   [ (xyz[b,idx]-new_xyz[b,j]) * (1/radius)  (3) | feats[b,idx,0:C] (C) | 0 ... ]
+ * rows of ld_out >= 3+C floats, zero padded (lets the next GEMM use a K that is a multiple of 4) */
+int bd_group_rows(const float *xyz, int ld_xyz, const float *feats, int ld_feats, int C,
+                  const float *new_xyz, const int *idx, int B, int n, int m, int ns, float radius,
+                  float *out, int ld_out, bd_stream_t stream);
+
+/* F.max_pool2d over nsample (pointnet2_modules.py:255): out[r, c] = max_s in[r*ns+s, c] */
+int bd_maxpool_rows(const float *in, int rows_out, int ns, int C, float *out, bd_stream_t stream);
+
+/* PointnetFPModule.forward up to the concat (pointnet2_modules.py:393-408), token-major:
+ * w = 1/(sqrt(dist2)+1e-8) normalised over the 3 neighbours;
+ * out[b,j,:] = [ sum_t w_t * known_feats[b,idx_t,0:C2] | unknown_feats[b,j,0:C1] ] */
+int bd_fp_interp_concat(const float *dist2, const int *idx, const float *known_feats, int C2,
+                        const float *unknown_feats, int C1, int B, int n, int m, float *out,
+                        bd_stream_t stream);
+
+/* Y = act( (A [+ A2]) · Wᵀ + bias ) : A (M,K) lda, A2 optional same shape (lda2), W (N,K)
+ * row-major (torch Linear / 1x1-conv weight, BatchNorm folded by the host), bias (N) or NULL,
+ * Y (M,N) ldy.  relu != 0 applies max(.,0).  fp32 SIMT path (1e-3 parity gate). */
+int bd_linear_f32(const float *A, int lda, const float *A2, int lda2, const float *W,
+                  const float *bias, float *Y, int ldy, int M, int N, int K, int relu,
+                  bd_stream_t stream);
+
+/* Y[r,:] = LayerNorm(X[r,:] + R[r,:]) * gamma + beta   (R may be NULL), rows of D floats,
+ * biased variance, eps inside the sqrt (torch.nn.LayerNorm). */
+int bd_add_layernorm_f32(const float *X, const float *R, const float *gamma, const float *beta,
+                         float *Y, int M, int D, float eps, bd_stream_t stream);
+
+/* Multi-head attention core of nn.MultiheadAttention (eval):
+ * O[b,i,h*hd:(h+1)*hd] = softmax_j( scale * <Q[b,i,h,:], K[b,j,h,:]> + mask ) · V[b,j,h,:]
+ * Q rows: Q + b*sq_b + i*ldq (+ h*hd), likewise K, V, O.  key_padding_mask (B,Lk) bytes,
+ * nonzero = ignore (-inf), may be NULL.  A fully masked row yields NaN like the reference. */
+int bd_attention_f32(const float *Q, int ldq, long long sq_b, const float *K, int ldk,
+                     long long sk_b, const float *V, int ldv, long long sv_b,
+                     const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
+                     int B, int H, int Lq, int Lk, int hd, float scale, bd_stream_t stream);
+
+/* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n
+ * logits, indices of the k largest sigmoid values, descending, ties -> lower index. n <= 4096 */
+int bd_topk_sigmoid(const float *logits, int B, int n, int k, int *idx, bd_stream_t stream);
+
+/* F.normalize(x, p=2, dim=-1, eps=1e-12) on rows of D floats (in place allowed). */
+int bd_l2_normalize_rows(const float *X, float *Y, int M, int D, bd_stream_t stream);
+
+/* out[r, 0:w] = table[ids[r], 0:w]  (nn.Embedding lookup, int64 ids). */
+int bd_embedding_rows(const float *table, int w, const long long *ids, int M, float *out,
+                      int ld_out, bd_stream_t stream);
+
+/* center = base_xyz + residual ; generic Y = X1 + X2 on (M,w) with leading dims. */
+int bd_add_rows(const float *X1, int ld1, const float *X2, int ld2, float *Y, int ldy, int M, int w,
+                bd_stream_t stream);
+
+/* Y[r,:] = [ X1[r,0:w1] | X2[r,0:w2] ]  — query_pos = cat(base_xyz, base_size) (models/bdetr.py:287) */
+int bd_concat_rows(const float *X1, int ld1, int w1, const float *X2, int ld2, int w2, float *Y,
+                   int ldy, int M, bd_stream_t stream);
+
+/* out[b, c, j] = in[b, j, c] — token-major (B,n,C) -> channel-major (B,C,n) for the
+ * end_points entries the reference returns channel-major (backbone_module.py:118-139). */
+int bd_transpose_rows(const float *in, int B, int n, int C, float *out, bd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUTD_B200_H_ */
