@@ -51,11 +51,17 @@ __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { ret
 
 // Squared distance with the contraction pattern of the reference's compiled kernels
 // (sm_100 SASS of ball_query_gpu.cu / sampling_gpu.cu / interpolate_gpu.cu:
-//  FMUL dx,dx ; FFMA dy,dy ; FFMA dz,dz).  Written with explicit intrinsics so the result
+//  FMUL dy,dy ; FFMA dx,dx ; FFMA dz,dz — for a*a + b*b the compiler multiplies the second
+//  product and fuses the first).  Written with explicit intrinsics so the result
 //  does not depend on this file's compile flags.
 __device__ __forceinline__ float sqdist_ref(float ax, float ay, float az, float bx, float by, float bz) {
   const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
-  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// |p|^2 as compiled in the reference FPS kernel (sampling_gpu.cu:104).
+__device__ __forceinline__ float sqnorm_ref(float x, float y, float z) {
+  return __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
 }
 
 }  // namespace bd

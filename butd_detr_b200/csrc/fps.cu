@@ -120,7 +120,7 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
     if (valid) {
       const float *p = xyz + static_cast<long long>(k) * ld;
       x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-      const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      const float mag = bd::sqnorm_ref(x, y, z);
       valid = !(static_cast<double>(mag) <= 1e-3);  // sampling_gpu.cu:105-106 (double compare)
     }
     px[i] = x, py[i] = y, pz[i] = z;
@@ -208,7 +208,7 @@ fps_streaming_kernel(const float *__restrict__ xyz, int ld, long long bstride, i
   for (int k = tid; k < N; k += FPS_THREADS) {
     const float *p = xyz + static_cast<long long>(k) * ld;
     const float x = p[0], y = p[1], z = p[2];
-    const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+    const float mag = bd::sqnorm_ref(x, y, z);
     tmp[k] = (static_cast<double>(mag) <= 1e-3) ? -2.0f : 1e10f;
   }
   if (tid == 0) idx_out[0] = 0;

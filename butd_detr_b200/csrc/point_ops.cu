@@ -163,9 +163,9 @@ __global__ void three_interpolate_kernel(const float *__restrict__ points, const
   const int *ii = idx + (static_cast<long long>(b) * n + j) * 3;
   const float *w = weight + (static_cast<long long>(b) * n + j) * 3;
   const float *src = points + (static_cast<long long>(b) * C + c) * m;
-  // FMUL, FFMA, FFMA as in the reference's compiled kernel (interpolate_gpu.cu:103-105)
+  // FMUL(p2,w2), FFMA(p1,w1), FFMA(p3,w3) as in the reference's compiled kernel (interpolate_gpu.cu:103-105)
   out[(static_cast<long long>(b) * C + c) * n + j] =
-      __fmaf_rn(__ldg(src + ii[2]), w[2], __fmaf_rn(__ldg(src + ii[1]), w[1], __fmul_rn(__ldg(src + ii[0]), w[0])));
+      __fmaf_rn(__ldg(src + ii[2]), w[2], __fmaf_rn(__ldg(src + ii[0]), w[0], __fmul_rn(__ldg(src + ii[1]), w[1])));
 }
 
 __global__ void three_interpolate_grad_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx,
@@ -257,7 +257,7 @@ __global__ void fp_interp_concat_kernel(const float *__restrict__ dist2, const i
   const float p0 = __ldg(kf + static_cast<long long>(__ldg(idx + r * 3 + 0)) * C2);
   const float p1 = __ldg(kf + static_cast<long long>(__ldg(idx + r * 3 + 1)) * C2);
   const float p2 = __ldg(kf + static_cast<long long>(__ldg(idx + r * 3 + 2)) * C2);
-  out[e] = __fmaf_rn(p2, w2, __fmaf_rn(p1, w1, __fmul_rn(p0, w0)));
+  out[e] = __fmaf_rn(p2, w2, __fmaf_rn(p0, w0, __fmul_rn(p1, w1)));
 }
 
 __global__ void transpose_rows_kernel(const float *__restrict__ in, int n, int C, float *__restrict__ out) {

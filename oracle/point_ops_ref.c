@@ -8,9 +8,10 @@
  *
  * Floating-point contract: the reference is compiled by nvcc with the default -fmad=true,
  * and the sm_100 SASS of the unmodified sources (oracle/build_ref_ext.py + cuobjdump) shows
- *     d  = FFMA(dz,dz, FFMA(dy,dy, FMUL(dx,dx)))          (FPS, ball query, three_nn)
- *     mag= FFMA(z,z,  FFMA(y,y,  FMUL(x,x)))  then a DOUBLE compare against 1e-3   (FPS)
- *     out= FFMA(p3,w3, FFMA(p2,w2, FMUL(p1,w1)))          (three_interpolate)
+ *     d  = FFMA(dz,dz, FFMA(dx,dx, FMUL(dy,dy)))          (FPS, ball query, three_nn)
+ *     mag= FFMA(z,z,  FFMA(x,x,  FMUL(y,y)))  then a DOUBLE compare against 1e-3   (FPS)
+ *     out= FFMA(p3,w3, FFMA(p1,w1, FMUL(p2,w2)))          (three_interpolate)
+ * (for a*a + b*b the compiler multiplies the SECOND product and fuses the first into it)
  * so those contractions are written here with explicit fmaf(); compile with
  * -ffp-contract=off so the C compiler adds none of its own.
  *
@@ -40,7 +41,7 @@ int orc_opt_n_threads(int work_size) {
 
 static inline float sqdist_fma(float ax, float ay, float az, float bx, float by, float bz) {
   const float dx = ax - bx, dy = ay - by, dz = az - bz;
-  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* sampling_gpu.cu:74-178 (kernel), sampling.cpp:70-91 (host: temp = 1e10, idx zeros).
@@ -62,7 +63,7 @@ int orc_fps(const float *xyz, int B, int N, int m, int *idx) {
     for (int k = 0; k < N; ++k) {
       temp[k] = 1e10f;
       const float x = p[3 * k], y = p[3 * k + 1], z = p[3 * k + 2];
-      const float mag = fmaf(z, z, fmaf(y, y, x * x));
+      const float mag = fmaf(z, z, fmaf(x, x, y * y));
       skip[k] = ((double)mag <= 1e-3) ? 1 : 0; /* :105-106, double compare */
     }
     int old = 0;
@@ -212,7 +213,7 @@ int orc_three_interpolate(const float *points, const int *idx, const float *weig
         const int *ii = idx + ((size_t)b * n + j) * 3;
         const float *w = weight + ((size_t)b * n + j) * 3;
         out[((size_t)b * C + c) * n + j] =
-            fmaf(src[ii[2]], w[2], fmaf(src[ii[1]], w[1], src[ii[0]] * w[0]));
+            fmaf(src[ii[2]], w[2], fmaf(src[ii[0]], w[0], src[ii[1]] * w[1]));
       }
     }
   return 0;

@@ -150,7 +150,8 @@ def test_group_maxpool_fp_rows_match_oracle(cuda_lib, oracle_lib):
     idx = oracle_lib.ball_query(new_xyz, xyz, 0.4, 16).cuda()
     feats_tm = feats.transpose(1, 2).contiguous().cuda()
     out = torch.empty(2 * 100 * 16, 12, device="cuda")
-    cuda_lib.call("bd_group_rows", xyz.cuda().data_ptr(), 3, feats_tm.data_ptr(), 7, 7, new_xyz.cuda().data_ptr(),
+    xyz_d, new_xyz_d = xyz.cuda(), new_xyz.cuda()
+    cuda_lib.call("bd_group_rows", xyz_d.data_ptr(), 3, feats_tm.data_ptr(), 7, 7, new_xyz_d.data_ptr(),
                   idx.data_ptr(), 2, 2000, 100, 16, 0.4, out.data_ptr(), 12)
     got = out.view(2, 100, 16, 12)
     torch.testing.assert_close(got[..., :10].permute(0, 3, 1, 2).cpu(), want, rtol=1e-6, atol=1e-6)
@@ -167,7 +168,8 @@ def test_group_maxpool_fp_rows_match_oracle(cuda_lib, oracle_lib):
     w = (rec / rec.sum(2, keepdim=True)).contiguous()
     want = torch.cat([oracle_lib.three_interpolate(kf, i3, w), uf], 1)      # (B,14,512)
     x = torch.empty(2 * 512, 14, device="cuda")
-    cuda_lib.call("bd_fp_interp_concat", d2.cuda().data_ptr(), i3.cuda().data_ptr(),
-                  kf.transpose(1, 2).contiguous().cuda().data_ptr(), 9,
-                  uf.transpose(1, 2).contiguous().cuda().data_ptr(), 5, 2, 512, 256, x.data_ptr())
+    d2_d, i3_d = d2.cuda(), i3.cuda()
+    kf_d, uf_d = kf.transpose(1, 2).contiguous().cuda(), uf.transpose(1, 2).contiguous().cuda()
+    cuda_lib.call("bd_fp_interp_concat", d2_d.data_ptr(), i3_d.data_ptr(), kf_d.data_ptr(), 9, uf_d.data_ptr(), 5,
+                  2, 512, 256, x.data_ptr())
     torch.testing.assert_close(x.view(2, 512, 14).transpose(1, 2).cpu(), want, rtol=1e-6, atol=1e-6)
