@@ -85,11 +85,53 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_profiler = None
+
+
+class Profiler:
+    """Per-launch CUDA-event timing of every C-ABI call made while active (eager launches only).
+    Events are recorded on the stream the kernel is launched on.  Keys are the entry point plus
+    its integer size arguments, e.g. `bd_fps(6, 8, 50000, 2048)`."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _profiler
+        _profiler = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profiler
+        _profiler = None
+
+    def table(self):
+        """[{name, launches, total_ms, mean_ms, share}] sorted by total time (call after a sync)."""
+        agg = {}
+        for key, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(key, [0, 0.0])
+            a[0] += 1
+            a[1] += ms
+        total = sum(a[1] for a in agg.values()) or 1.0
+        rows = [{"name": k, "launches": n, "total_ms": t, "mean_ms": t / n, "share": t / total}
+                for k, (n, t) in agg.items()]
+        return sorted(rows, key=lambda r: -r["total_ms"])
+
+
 def call(name, *args):
     """Invoke `name(*args, current_stream)`; raise RuntimeError with the library's message on failure."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
+    if _profiler is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        e1.record()
+        sizes = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 24))
+        _profiler.records.append((f"{name}{sizes}", e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
     launch_count += 1
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {lib.bd_last_error().decode()}")

@@ -258,14 +258,14 @@ class ForwardEngine:
         return h.view(B, L, -1)
 
     # ---- point ops
-    def fps(self, xyz, ld, B, N, m):
-        idx = self._empty(B, m, dtype=torch.int32)
+    def fps(self, xyz, ld, B, N, m, out=None):
+        idx = out if out is not None else self._empty(B, m, dtype=torch.int32)
         tmp = self._empty(B, N) if N > _lib.load().bd_fps_resident_capacity() else None
         _lib.call("bd_fps", xyz.data_ptr(), ld, B, N, m, _lib.ptr(tmp), idx.data_ptr())
         return idx
 
-    def gather_rows(self, src, ld_src, idx, B, n_src, m, w):
-        out = self._empty(B, m, w)
+    def gather_rows(self, src, ld_src, idx, B, n_src, m, w, out=None):
+        out = out if out is not None else self._empty(B, m, w)
         _lib.call("bd_gather_rows", src.data_ptr(), ld_src, idx.data_ptr(), B, n_src, m, w, out.data_ptr(), w)
         return out
 
@@ -310,14 +310,16 @@ class ForwardEngine:
         # coordinates of levels 2-4 only depend on xyz: run their (serial) FPS chain on a side
         # stream while the main stream does ball query + MLPs
         levels = {"sa1": (xyz1, inds1)}
+        for name, m, _, _ in SA_CFG[1:]:  # allocated on `main`, written on the side stream
+            levels[name] = (self._empty(B, m, 3), self._empty(B, m, dtype=torch.int32))
         ready = {}
         self.side_stream.wait_stream(main)
         with torch.cuda.stream(self.side_stream):
             prev, n_prev = xyz1, SA_CFG[0][1]
             for name, m, _, _ in SA_CFG[1:]:
-                inds = self.fps(prev, 3, B, n_prev, m)
-                nxt = self.gather_rows(prev, 3, inds, B, n_prev, m, 3)
-                levels[name] = (nxt, inds)
+                nxt, inds = levels[name]
+                self.fps(prev, 3, B, n_prev, m, out=inds)
+                self.gather_rows(prev, 3, inds, B, n_prev, m, 3, out=nxt)
                 ready[name] = self.side_stream.record_event()
                 prev, n_prev = nxt, m
         for name, m, radius, ns in SA_CFG:
@@ -331,8 +333,7 @@ class ForwardEngine:
                 ep[name + "_inds"] = inds
             xyz, ld_xyz, n = new_xyz, 3, m
             feats, ld_feats, C = f, f.shape[-1], f.shape[-1]
-        for t in levels.values():  # tensors produced on the side stream are consumed on `main`
-            t[0].record_stream(main), t[1].record_stream(main)
+        main.wait_stream(self.side_stream)  # join (also required to end a CUDA-graph capture)
         f = self.fp_level("fp1", ep["sa3_xyz"], ep["sa4_xyz"], ep["sa3_features_tm"], ep["sa4_features_tm"], B, 512, 256)
         f = self.fp_level("fp2", ep["sa2_xyz"], ep["sa3_xyz"], ep["sa2_features_tm"], f, B, 1024, 512)
         for name in ("sa1", "sa2", "sa3", "sa4"):
@@ -341,6 +342,40 @@ class ForwardEngine:
         ep["fp2_xyz"] = ep["sa2_xyz"]
         ep["fp2_inds"] = ep["sa1_inds"][:, :ep["fp2_xyz"].shape[1]]
         return f  # (B, 1024, 288) token-major seed features
+
+    # ---- CUDA-graph replay of the whole forward
+    @torch.no_grad()
+    def forward_graphed(self, inputs):
+        """Same result as forward(), replayed from a CUDA graph captured per input-shape
+        signature.  Inputs are copied into static buffers; the returned tensors are the graph's
+        static outputs and are overwritten by the next call with the same shapes."""
+        keys = [k for k in ("point_clouds", "text_hidden", "text_attention_mask", "det_boxes", "det_bbox_label_mask",
+                            "det_class_ids") if k in inputs]
+        sig = tuple((k, tuple(inputs[k].shape), inputs[k].dtype) for k in keys)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        entry = self._graphs.get(sig)
+        if entry is None:
+            static_in = {k: inputs[k].detach().clone().contiguous() for k in keys}
+            with torch.cuda.device(self.device):
+                warm = torch.cuda.Stream()
+                warm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(warm):  # warm-up off the default stream (lazy module loads etc.)
+                    self.forward(static_in)
+                torch.cuda.current_stream().wait_stream(warm)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count
+                with torch.cuda.graph(graph):
+                    static_out = self.forward(static_in)
+                entry = (graph, static_in, static_out, _lib.launch_count - n0)
+            self._graphs[sig] = entry
+        graph, static_in, static_out, n_launch = entry
+        for k in keys:
+            static_in[k].copy_(inputs[k], non_blocking=True)
+        graph.replay()
+        _lib.launch_count += n_launch
+        return dict(static_out)
 
     # ---- whole forward
     @torch.no_grad()

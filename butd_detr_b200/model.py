@@ -58,7 +58,7 @@ class BeaUTyDETR(nn.Module):
     def __init__(self, num_class=256, num_obj_class=485, input_feature_dim=3, num_queries=256,
                  num_decoder_layers=6, self_position_embedding='loc_learned', contrastive_align_loss=True,
                  d_model=288, butd=True, pointnet_ckpt=None, self_attend=True, *,
-                 text_encoder="roberta-base", num_encoder_layers=3):
+                 text_encoder="roberta-base", num_encoder_layers=3, cuda_graph=False):
         super().__init__()
         if self_position_embedding not in ("none", "xyz_learned", "loc_learned"):
             raise NotImplementedError(self_position_embedding)
@@ -78,6 +78,7 @@ class BeaUTyDETR(nn.Module):
         self._attach_text_encoder(text_encoder)
         if input_feature_dim == 3 and pointnet_ckpt is not None:  # bdetr.py:67-70
             self.backbone_net.load_state_dict(torch.load(pointnet_ckpt), strict=False)
+        self.cuda_graph = cuda_graph  # replay the forward from a CUDA graph (static output buffers)
         self._engine = None
         self._engine_key = None
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_engine())
@@ -271,7 +272,10 @@ class BeaUTyDETR(nn.Module):
         if self.butd:
             for k in ("det_boxes", "det_bbox_label_mask", "det_class_ids"):
                 eng_in[k] = inputs[k]
-        end_points = self.engine().forward(eng_in, overrides)
+        if self.cuda_graph and overrides is None:
+            end_points = self.engine().forward_graphed(eng_in)
+        else:
+            end_points = self.engine().forward(eng_in, overrides)
         if tokenized is not None:
             end_points["tokenized"] = tokenized
         return end_points
