@@ -57,6 +57,28 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
+def tc_tiling(N, K):
+    """(BN, KC, n_chunks) used by bd_linear_tc for an (N, K) weight: BN <= 160 columns per CTA
+    (multiple of 16), K consumed in equal chunks of KC <= 288 (multiple of 16)."""
+    nt = -(-N // 160)
+    BN = _round_up(-(-N // nt), 16)
+    n_chunks = -(-K // 288)
+    KC = _round_up(-(-K // n_chunks), 16)
+    return BN, KC, n_chunks
+
+
+def pack_weight_tc(W):
+    """(N, K) fp32 -> bf16 blocks in the tensor-core kernels' shared-memory layout
+    Wp[n_tile][k_chunk][BN/8][KC/8][8 rows][8 k] (see csrc/tc_common.cuh), zero padded."""
+    N, K = W.shape
+    BN, KC, n_chunks = tc_tiling(N, K)
+    nt = -(-N // BN)
+    Wp = W.new_zeros(nt * BN, n_chunks * KC)
+    Wp[:N, :K] = W
+    Wp = Wp.view(nt, BN // 8, 8, n_chunks, KC // 8, 8).permute(0, 3, 1, 4, 2, 5)
+    return Wp.contiguous().to(torch.bfloat16), (BN, KC, n_chunks)
+
+
 class PackedWeights:
     """Device-resident, BN-folded, GEMM-ready weights (fp32 masters)."""
 

@@ -128,6 +128,16 @@ int bd_linear_f32(const float *A, int lda, const float *A2, int lda2, const floa
                   const float *bias, float *Y, int ldy, int M, int N, int K, int relu,
                   bd_stream_t stream);
 
+/* Same contract as bd_linear_f32, computed on the 5th-gen tensor cores (tcgen05.mma, bf16
+ * operands, fp32 accumulation in TMEM).  A is converted to bf16 while it is staged; `Wp` is the
+ * weight pre-packed by the host (butd_detr_b200.engine.pack_weight_tc) into the kernel's shared
+ * memory layout:  Wp[n_tile][k_chunk][BN/8][KC/8][8 rows][8 k] bf16, zero padded, where
+ * n_tile = n / BN, k_chunk = k / KC.  KC: multiple of 16, <= 288; BN: multiple of 16, <= 256;
+ * (128 + BN) * KC * 2 bytes must fit 227 KB of shared memory. */
+int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp,
+                 const float *bias, float *Y, int ldy, int M, int N, int K, int KC, int n_chunks,
+                 int BN, int relu, bd_stream_t stream);
+
 /* Y[r,:] = LayerNorm(X[r,:] + R[r,:]) * gamma + beta   (R may be NULL), rows of D floats,
  * biased variance, eps inside the sqrt (torch.nn.LayerNorm). */
 int bd_add_layernorm_f32(const float *X, const float *R, const float *gamma, const float *beta,

@@ -1,0 +1,52 @@
+"""GPU numerics of the tcgen05 (bf16 operands, fp32 accumulate) kernels vs PyTorch on the same
+bf16-rounded operands.  Tolerance: accumulation-order noise only (1e-4 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("M,N,K,relu,add", [(128, 64, 16, False, False), (128, 144, 288, False, False),
+                                             (256, 288, 288, True, False), (1024, 576, 288, False, True),
+                                             (80, 288, 288, False, False), (300, 256, 288, True, False),
+                                             (1000, 128, 132, True, False), (4099, 64, 8, True, False),
+                                             (513, 160, 768, False, False), (512, 256, 512, True, False),
+                                             (200, 864, 288, False, False), (77, 64, 288, False, False)])
+def test_linear_tc(cuda_lib, M, N, K, relu, add):
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    A2 = torch.randn(M, K, device="cuda", generator=g) if add else None
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    Wp, (BN, KC, nch) = pack_weight_tc(W)
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    cuda_lib.call("bd_linear_tc", A.data_ptr(), K, cuda_lib.ptr(A2), K, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), N,
+                  M, N, K, KC, nch, BN, int(relu))
+    torch.cuda.synchronize()
+    a = (A + A2 if add else A).bfloat16().double()
+    want = F.linear(a, W.bfloat16().double(), b.double())
+    want = (want.relu() if relu else want).float()
+    torch.testing.assert_close(Y, want, rtol=1e-4, atol=1e-4)
+
+
+def test_linear_tc_strided(cuda_lib):
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(9)
+    big = torch.randn(300, 864, device="cuda", generator=g)
+    W = torch.randn(160, 288, device="cuda", generator=g) / 17
+    Wp, (BN, KC, nch) = pack_weight_tc(W)
+    out = torch.zeros(300, 288, device="cuda")
+    x = big[:, 288:576]
+    cuda_lib.call("bd_linear_tc", x.data_ptr(), 864, None, 0, Wp.data_ptr(), None, out[:, 128:].data_ptr(), 288,
+                  300, 160, 288, KC, nch, BN, 0)
+    want = (x.bfloat16().double() @ W.bfloat16().double().t()).float()
+    torch.testing.assert_close(out[:, 128:], want, rtol=1e-4, atol=1e-4)
+    assert float(out[:, :128].abs().max()) == 0.0
