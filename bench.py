@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(n_points=50000, n_seeds=1024, num_queries=256, n_tokens=80, n_boxes=132, d_model=288,
                 num_encoder_layers=3, num_decoder_layers=6)
 METRIC = "scenes/sec fwd (50k pts, 256 queries, 80 tok)"
+DTYPES = {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (bf16 hi+lo split operands on tcgen05, fp32 accumulate; "
+                                                  "attention core fp32)"}
 GRADED = ["center", "pred_size", "sem_cls_scores", "proj_queries"]
 
 
@@ -145,6 +147,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of CUDA-graph replay")
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
+                    help="fp32 = SIMT kernels; bf16x3 = tcgen05 with bf16 hi/lo split operands (default)")
     ap.add_argument("--cpu-scenes", type=int, default=3, help="scenes timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -161,7 +165,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
-    model = BeaUTyDETR(text_encoder=None, cuda_graph=not args.no_graph)
+    model = BeaUTyDETR(text_encoder=None, cuda_graph=not args.no_graph, precision=args.precision)
     synth.fill_state_dict_(model.state_dict(), 0)
     model = model.to(dev).eval()
 
@@ -268,10 +272,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": scenes / (ms_total * 1e-3), "unit": "scenes/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
                 "config": {"workload": "configs[1]: 50k-pt ScanNet-shaped scene, 1024 seeds, 256 queries, 80 tokens, "
                                        "132 boxes, d=288, 3 enc + 6 dec layers, eval forward (RoBERTa output synthetic)",
-                           "batch_per_step_per_gpu": B, "precision": "fp32 (SIMT) — bf16 tcgen05 path not enabled",
+                           "batch_per_step_per_gpu": B, "precision": args.precision,
                            "cuda_graph": not args.no_graph, "parallelism": f"dp{world} (independent replicas)",
                            "l2": f"inputs rotate through {n_pool} distinct scenes/GPU "
                                  f"({n_pool * bytes_per_scene / 1e6:.0f} MB > 126 MB L2)"},

@@ -5,8 +5,8 @@
 //        the optional second operand A2 (positional embedding) is added during staging.
 //   Wp : weights PRE-PACKED by the host into that same layout, one contiguous block per
 //        (n-tile, k-chunk), so each block arrives with a single cp.async.bulk (TMA engine)
-//        signalled on an mbarrier.  Packing: Wp[nt][kc][BN/8][KC/8][8 rows][8 k] bf16,
-//        zero padded to BN x KC.
+//        signalled on an mbarrier.  Packing: Wp[nt][kc][part][BN/8][KC/8][8 rows][8 k] bf16,
+//        zero padded to BN x KC; part = {hi} (split 1) or {hi, lo} (split 3, bf16x3).
 //   D  : 128 x BN fp32 accumulator in TMEM (tcgen05.mma cta_group::1, M = 128, K = 16 per
 //        instruction, issued by one thread); epilogue tcgen05.ld -> bias / ReLU -> fp32 store.
 //
@@ -23,7 +23,7 @@ constexpr int TC_THREADS = 256;
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ A2, int lda2,
                  const __nv_bfloat16 *__restrict__ Wp, const float *__restrict__ bias, float *__restrict__ Y, int ldy,
-                 int M, int N, int K, int KC, int n_chunks, int BN, int relu) {
+                 int M, int N, int K, int KC, int n_chunks, int BN, int relu, int split) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_w, bar_mma;
   __shared__ uint32_t tmem_base_s;
@@ -31,7 +31,11 @@ linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TC_BM;
   const int nt = blockIdx.y;
-  const uint32_t a_bytes = TC_BM * KC * 2, w_bytes = static_cast<uint32_t>(BN) * KC * 2;
+  // split == 3: every fp32 operand x is carried as bf16 hi + bf16 lo (x ~ hi + lo to 16 mantissa
+  // bits) and D += Ahi*Whi + Alo*Whi + Ahi*Wlo, i.e. fp32-grade products at 3 MMAs per k-step.
+  const uint32_t parts = split == 3 ? 2u : 1u;
+  const uint32_t a_part = TC_BM * KC * 2, w_part = static_cast<uint32_t>(BN) * KC * 2;
+  const uint32_t a_bytes = a_part * parts, w_bytes = w_part * parts;
   unsigned char *sA = smem;
   unsigned char *sW = smem + a_bytes;
   const uint32_t sbo = (KC / 8) * 128;
@@ -54,7 +58,7 @@ linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__
     if (c > 0) tc::mbar_wait(tc::smem_u32(&bar_mma), (c - 1) & 1);  // previous chunk's MMAs have read smem
     if (tid == 0) {
       tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_w), w_bytes);
-      tc::bulk_g2s(tc::smem_u32(sW), Wp + (static_cast<size_t>(nt) * n_chunks + c) * BN * KC, w_bytes,
+      tc::bulk_g2s(tc::smem_u32(sW), Wp + (static_cast<size_t>(nt) * n_chunks + c) * BN * KC * parts, w_bytes,
                    tc::smem_u32(&bar_w));
     }
     // stage A: each thread converts 8 consecutive k of one row (32 B in, 16 B out).  Lanes are
@@ -91,6 +95,14 @@ linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__
       pk.x = tc::pack_bf16x2(v[0], v[1]), pk.y = tc::pack_bf16x2(v[2], v[3]);
       pk.z = tc::pack_bf16x2(v[4], v[5]), pk.w = tc::pack_bf16x2(v[6], v[7]);
       *reinterpret_cast<uint4 *>(sA + tc::canon_off(r, ch, sbo)) = pk;
+      if (parts == 2) {
+        float lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+        pk.x = tc::pack_bf16x2(lo[0], lo[1]), pk.y = tc::pack_bf16x2(lo[2], lo[3]);
+        pk.z = tc::pack_bf16x2(lo[4], lo[5]), pk.w = tc::pack_bf16x2(lo[6], lo[7]);
+        *reinterpret_cast<uint4 *>(sA + a_part + tc::canon_off(r, ch, sbo)) = pk;
+      }
     }
     tc::fence_proxy_async_smem();
     __syncthreads();
@@ -102,6 +114,10 @@ linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__
         const uint64_t da = tc::smem_desc(a0 + s * 256, 128, sbo);
         const uint64_t db = tc::smem_desc(w0 + s * 256, 128, sbo);
         tc::mma_bf16(tmem, da, db, idesc, (c > 0 || s > 0) ? 1u : 0u);
+        if (parts == 2) {
+          tc::mma_bf16(tmem, tc::smem_desc(a0 + a_part + s * 256, 128, sbo), db, idesc, 1u);
+          tc::mma_bf16(tmem, da, tc::smem_desc(w0 + w_part + s * 256, 128, sbo), idesc, 1u);
+        }
       }
       tc::mma_commit(tc::smem_u32(&bar_mma));
     }
@@ -141,7 +157,7 @@ linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__
 
 extern "C" int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp, const float *bias,
                             float *Y, int ldy, int M, int N, int K, int KC, int n_chunks, int BN, int relu,
-                            bd_stream_t stream) {
+                            int split, bd_stream_t stream) {
   BD_REQUIRE(A && Wp && Y, "bd_linear_tc: null pointer");
   BD_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldy >= N && (!A2 || lda2 >= K), "bd_linear_tc: bad sizes");
   BD_REQUIRE(KC % 16 == 0 && KC >= 16 && KC <= 288 && n_chunks >= 1 && n_chunks * KC >= K,
@@ -149,7 +165,8 @@ extern "C" int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, 
   BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "bd_linear_tc: BN must be a multiple of 16 in [16,256]");
   const int n_tiles = bd::ceil_div(N, BN);
   BD_REQUIRE(n_tiles <= 65535, "bd_linear_tc: N too large");
-  const size_t smem = static_cast<size_t>(TC_BM + BN) * KC * 2;
+  BD_REQUIRE(split == 1 || split == 3, "bd_linear_tc: split must be 1 (bf16) or 3 (bf16x3)");
+  const size_t smem = static_cast<size_t>(TC_BM + BN) * KC * 2 * (split == 3 ? 2 : 1);
   BD_REQUIRE(smem <= 226 * 1024, "bd_linear_tc: tile does not fit shared memory");
   static thread_local bool configured = false;
   if (!configured) {
@@ -159,7 +176,7 @@ extern "C" int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, 
   }
   dim3 grid(bd::ceil_div(M, TC_BM), n_tiles);
   linear_tc_kernel<<<grid, TC_THREADS, smem, bd::as_stream(stream)>>>(
-      A, lda, A2, lda2, static_cast<const __nv_bfloat16 *>(Wp), bias, Y, ldy, M, N, K, KC, n_chunks, BN, relu);
+      A, lda, A2, lda2, static_cast<const __nv_bfloat16 *>(Wp), bias, Y, ldy, M, N, K, KC, n_chunks, BN, relu, split);
   BD_CHECK_LAUNCH("bd_linear_tc");
   return BD_OK;
 }

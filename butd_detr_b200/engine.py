@@ -57,26 +57,32 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
-def tc_tiling(N, K):
+def tc_tiling(N, K, split=1):
     """(BN, KC, n_chunks) used by bd_linear_tc for an (N, K) weight: BN <= 160 columns per CTA
-    (multiple of 16), K consumed in equal chunks of KC <= 288 (multiple of 16)."""
+    (multiple of 16), K consumed in equal chunks of KC (multiple of 16) <= 288 (split 1) or
+    <= 144 (split 3: hi and lo parts of both operands are staged)."""
     nt = -(-N // 160)
     BN = _round_up(-(-N // nt), 16)
-    n_chunks = -(-K // 288)
+    kc_max = 288 if split == 1 else 144
+    n_chunks = -(-K // kc_max)
     KC = _round_up(-(-K // n_chunks), 16)
     return BN, KC, n_chunks
 
 
-def pack_weight_tc(W):
+def pack_weight_tc(W, split=1):
     """(N, K) fp32 -> bf16 blocks in the tensor-core kernels' shared-memory layout
-    Wp[n_tile][k_chunk][BN/8][KC/8][8 rows][8 k] (see csrc/tc_common.cuh), zero padded."""
+    Wp[n_tile][k_chunk][part][BN/8][KC/8][8 rows][8 k] (see csrc/tc_common.cuh), zero padded;
+    part = {hi} or, for split 3, {hi, lo} with lo = bf16(W - hi)."""
     N, K = W.shape
-    BN, KC, n_chunks = tc_tiling(N, K)
+    BN, KC, n_chunks = tc_tiling(N, K, split)
     nt = -(-N // BN)
     Wp = W.new_zeros(nt * BN, n_chunks * KC)
     Wp[:N, :K] = W
-    Wp = Wp.view(nt, BN // 8, 8, n_chunks, KC // 8, 8).permute(0, 3, 1, 4, 2, 5)
-    return Wp.contiguous().to(torch.bfloat16), (BN, KC, n_chunks)
+    hi = Wp.to(torch.bfloat16)
+    parts = [hi] if split == 1 else [hi, (Wp - hi.float()).to(torch.bfloat16)]
+    P = torch.stack(parts, 0)  # (part, N_pad, K_pad)
+    P = P.view(len(parts), nt, BN // 8, 8, n_chunks, KC // 8, 8).permute(1, 4, 0, 2, 5, 3, 6)
+    return P.contiguous(), (BN, KC, n_chunks)
 
 
 class PackedWeights:
@@ -191,6 +197,11 @@ class ForwardEngine:
         _lib.load()
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items() if not k.startswith("text_encoder.")}
         self.W = PackedWeights(sd, self.cfg)
+        self.precision = cfg.get("precision", "fp32")
+        if self.precision not in ("fp32", "bf16", "bf16x3"):
+            raise ValueError("precision must be 'fp32' (SIMT), 'bf16' or 'bf16x3' (tcgen05)")
+        self.split = 3 if self.precision == "bf16x3" else 1
+        self._tc = {}  # key -> (packed bf16 weight, (BN, KC, n_chunks)), built on first use
         self.d_model = cfg["d_model"]
         self.n_heads = 8
         self.side_stream = torch.cuda.Stream(device=self.device)
@@ -207,8 +218,16 @@ class ForwardEngine:
         if out is None:
             out = self._empty(M, N)
         assert out.stride(1) == 1
-        _lib.call("bd_linear_f32", x.data_ptr(), x.stride(0), _lib.ptr(add), 0 if add is None else add.stride(0),
-                  W.data_ptr(), _lib.ptr(b), out.data_ptr(), out.stride(0), M, N, K, int(relu))
+        lda2 = 0 if add is None else add.stride(0)
+        if self.precision != "fp32" and N >= 16:  # tensor cores; the 1-/3-wide heads stay on the fp32 kernel
+            if key not in self._tc:
+                self._tc[key] = pack_weight_tc(W, self.split)
+            Wp, (BN, KC, n_chunks) = self._tc[key]
+            _lib.call("bd_linear_tc", x.data_ptr(), x.stride(0), _lib.ptr(add), lda2, Wp.data_ptr(), _lib.ptr(b),
+                      out.data_ptr(), out.stride(0), M, N, K, KC, n_chunks, BN, int(relu), self.split)
+        else:
+            _lib.call("bd_linear_f32", x.data_ptr(), x.stride(0), _lib.ptr(add), lda2, W.data_ptr(), _lib.ptr(b),
+                      out.data_ptr(), out.stride(0), M, N, K, int(relu))
         return out
 
     def add_ln(self, x, res, key, eps=LN_EPS, out=None):

@@ -58,7 +58,7 @@ class BeaUTyDETR(nn.Module):
     def __init__(self, num_class=256, num_obj_class=485, input_feature_dim=3, num_queries=256,
                  num_decoder_layers=6, self_position_embedding='loc_learned', contrastive_align_loss=True,
                  d_model=288, butd=True, pointnet_ckpt=None, self_attend=True, *,
-                 text_encoder="roberta-base", num_encoder_layers=3, cuda_graph=False):
+                 text_encoder="roberta-base", num_encoder_layers=3, cuda_graph=False, precision="fp32"):
         super().__init__()
         if self_position_embedding not in ("none", "xyz_learned", "loc_learned"):
             raise NotImplementedError(self_position_embedding)
@@ -73,7 +73,7 @@ class BeaUTyDETR(nn.Module):
                         num_queries=num_queries, num_decoder_layers=num_decoder_layers,
                         num_encoder_layers=num_encoder_layers, self_position_embedding=self_position_embedding,
                         contrastive_align_loss=contrastive_align_loss, d_model=d_model, butd=butd,
-                        self_attend=self_attend)
+                        self_attend=self_attend, precision=precision)
         self._build_tree()
         self._attach_text_encoder(text_encoder)
         if input_feature_dim == 3 and pointnet_ckpt is not None:  # bdetr.py:67-70

@@ -131,12 +131,15 @@ int bd_linear_f32(const float *A, int lda, const float *A2, int lda2, const floa
 /* Same contract as bd_linear_f32, computed on the 5th-gen tensor cores (tcgen05.mma, bf16
  * operands, fp32 accumulation in TMEM).  A is converted to bf16 while it is staged; `Wp` is the
  * weight pre-packed by the host (butd_detr_b200.engine.pack_weight_tc) into the kernel's shared
- * memory layout:  Wp[n_tile][k_chunk][BN/8][KC/8][8 rows][8 k] bf16, zero padded, where
- * n_tile = n / BN, k_chunk = k / KC.  KC: multiple of 16, <= 288; BN: multiple of 16, <= 256;
- * (128 + BN) * KC * 2 bytes must fit 227 KB of shared memory. */
+ * memory layout:  Wp[n_tile][k_chunk][part][BN/8][KC/8][8 rows][8 k] bf16, zero padded, where
+ * n_tile = n / BN, k_chunk = k / KC.  KC: multiple of 16, <= 288; BN: multiple of 16, <= 256.
+ * split = 1: plain bf16 operands (part = {hi}).  split = 3 ("bf16x3"): every fp32 operand is
+ * carried as bf16 hi + bf16 lo and D += Ahi*Whi + Alo*Whi + Ahi*Wlo (part = {hi, lo}), which
+ * restores fp32-grade products on the bf16 tensor pipe.  (128 + BN) * KC * 2 * parts bytes must
+ * fit 226 KB of shared memory. */
 int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp,
                  const float *bias, float *Y, int ldy, int M, int N, int K, int KC, int n_chunks,
-                 int BN, int relu, bd_stream_t stream);
+                 int BN, int relu, int split, bd_stream_t stream);
 
 /* Y[r,:] = LayerNorm(X[r,:] + R[r,:]) * gamma + beta   (R may be NULL), rows of D floats,
  * biased variance, eps inside the sqrt (torch.nn.LayerNorm). */

@@ -18,11 +18,11 @@ CFG = {  # must mirror tests/golden/make_model_golden.py
 TOL = 1e-3
 
 
-def build(name, cuda_lib):
+def build(name, cuda_lib, precision="fp32"):
     from butd_detr_b200 import BeaUTyDETR, synth
     c = CFG[name]
     model = BeaUTyDETR(num_queries=c["num_queries"], num_decoder_layers=c["dec"], num_encoder_layers=c["enc"],
-                       text_encoder=None)
+                       text_encoder=None, precision=precision)
     synth.fill_state_dict_(model.state_dict(), 0)
     model = model.cuda().eval()
     inputs = synth.synth_batch(c["seed"], c["batch"], c["n_points"], c["n_tokens"], c["n_boxes"])
@@ -98,3 +98,36 @@ def test_batch_rows_are_independent(cuda_lib):
     for k in ("last_center", "last_pred_size", "last_sem_cls_scores", "seeds_obj_cls_logits"):
         torch.testing.assert_close(full[k][1:2], one[k], rtol=0, atol=1e-5)
     assert torch.equal(full["sa1_inds"][1:2], one["sa1_inds"])
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_tensor_core_forward_matches_reference_golden(name, precision, tol, cuda_lib, golden_dir):
+    """Tensor-core modes (BASELINE.json configs[1]).  'bf16x3' (bf16 hi/lo split operands, three
+    tcgen05 MMAs per product, fp32 accumulation) is the shipped mode and must meet even the fp32
+    gate (1e-3, hence the 1e-2 bf16 gate with margin).  Plain single-pass 'bf16' operands land
+    at 1-2e-2 after ~30 stacked post-LN GEMM layers — just outside the 1e-2 gate — and is kept
+    only as a measured comparison point (sanity bound 5e-2).  Query selection is teacher-forced with the reference's indices (SURVEY.md §7 hard
+    part 3: 1e-2 perturbations reorder the near-tied top-k scores, which permutes per-query
+    outputs without changing their values); the selection agreement is reported."""
+    gold = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    model, inputs = build(name, cuda_lib, precision=precision)
+    dev_in = {k: v.cuda() for k, v in inputs.items()}
+    free = model(dev_in)
+    want_inds = gold["query_points_sample_inds"]
+    got_inds = free["query_points_sample_inds"].cpu().numpy()
+    agree = np.mean([len(set(a) & set(b)) / len(a) for a, b in zip(got_inds, want_inds)])
+    for k in ("sa1_inds", "sa2_inds"):
+        assert np.array_equal(free[k].cpu().numpy(), gold[k]), k      # point ops stay exact
+    ep = model(dev_in, overrides={"sample_inds": torch.from_numpy(want_inds)})
+    worst = {}
+    for k in gold.files:
+        if k.startswith("__") or gold[k].dtype.kind in "iub":
+            continue
+        worst[k] = float(np.abs(ep[k].float().cpu().numpy() - gold[k]).max())
+    graded = {k: v for k, v in worst.items() if k.endswith(("center", "pred_size", "sem_cls_scores", "proj_queries"))}
+    print(name, precision, ": top-k agreement %.3f, max abs err graded %.2e, all %.2e" % (
+        agree, max(graded.values()), max(worst.values())))
+    bad = {k: v for k, v in graded.items() if not v <= tol}
+    assert not bad, bad
+    assert agree > (0.98 if precision == "bf16x3" else 0.8)

@@ -19,22 +19,28 @@ def _g(seed):
                                              (1000, 128, 132, True, False), (4099, 64, 8, True, False),
                                              (513, 160, 768, False, False), (512, 256, 512, True, False),
                                              (200, 864, 288, False, False), (77, 64, 288, False, False)])
-def test_linear_tc(cuda_lib, M, N, K, relu, add):
+@pytest.mark.parametrize("split", [1, 3])
+def test_linear_tc(cuda_lib, M, N, K, relu, add, split):
     from butd_detr_b200.engine import pack_weight_tc
     g = _g(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g)
     A2 = torch.randn(M, K, device="cuda", generator=g) if add else None
     W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
     b = torch.randn(N, device="cuda", generator=g)
-    Wp, (BN, KC, nch) = pack_weight_tc(W)
+    Wp, (BN, KC, nch) = pack_weight_tc(W, split)
     Y = torch.full((M, N), float("nan"), device="cuda")
     cuda_lib.call("bd_linear_tc", A.data_ptr(), K, cuda_lib.ptr(A2), K, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), N,
-                  M, N, K, KC, nch, BN, int(relu))
+                  M, N, K, KC, nch, BN, int(relu), split)
     torch.cuda.synchronize()
-    a = (A + A2 if add else A).bfloat16().double()
-    want = F.linear(a, W.bfloat16().double(), b.double())
+    a = A + A2 if add else A
+    if split == 1:  # plain bf16 operands: compare with the same rounding applied
+        want = F.linear(a.bfloat16().double(), W.bfloat16().double(), b.double())
+        tol = 1e-4
+    else:           # bf16x3: fp32-grade
+        want = F.linear(a.double(), W.double(), b.double())
+        tol = 1e-4
     want = (want.relu() if relu else want).float()
-    torch.testing.assert_close(Y, want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(Y, want, rtol=tol, atol=tol)
 
 
 def test_linear_tc_strided(cuda_lib):
@@ -46,7 +52,7 @@ def test_linear_tc_strided(cuda_lib):
     out = torch.zeros(300, 288, device="cuda")
     x = big[:, 288:576]
     cuda_lib.call("bd_linear_tc", x.data_ptr(), 864, None, 0, Wp.data_ptr(), None, out[:, 128:].data_ptr(), 288,
-                  300, 160, 288, KC, nch, BN, 0)
+                  300, 160, 288, KC, nch, BN, 0, 1)
     want = (x.bfloat16().double() @ W.bfloat16().double().t()).float()
     torch.testing.assert_close(out[:, 128:], want, rtol=1e-4, atol=1e-4)
     assert float(out[:, :128].abs().max()) == 0.0
