@@ -1,182 +1,432 @@
-// bf16 tensor-core linear layer on tcgen05:  Y = act((A [+ A2]) · Wᵀ + bias)
+// Tensor-core linear layer on tcgen05:
+//     Y = act((A [+ A2]) · Wᵀ + bias)                       (plain epilogue)
+//     Y = LayerNorm(R + (A [+ A2]) · Wᵀ + bias) * g + b      (fused residual + LayerNorm epilogue)
 //
-//   A  : (M, K) fp32 row-major activations (token-major), converted to bf16 while being staged
-//        into shared memory in the canonical K-major core-matrix layout (tc_common.cuh);
-//        the optional second operand A2 (positional embedding) is added during staging.
+//   A  : (M, K) fp32 row-major activations (token-major), K % 8 == 0, 16-byte aligned rows.  They
+//        are converted to bf16 — a hi part, or hi + lo parts in the "bf16x3" mode — while being
+//        staged into shared memory in the 128-byte-swizzle K-major layout (tc_common.cuh).  A2
+//        (positional embedding) is added during staging.  Global loads are software-pipelined
+//        two k-chunks ahead through two register sets.
 //   Wp : weights PRE-PACKED by the host into that same layout, one contiguous block per
-//        (n-tile, k-chunk), so each block arrives with a single cp.async.bulk (TMA engine)
-//        signalled on an mbarrier.  Packing: Wp[nt][kc][part][BN/8][KC/8][8 rows][8 k] bf16,
-//        zero padded to BN x KC; part = {hi} (split 1) or {hi, lo} (split 3, bf16x3).
-//   D  : 128 x BN fp32 accumulator in TMEM (tcgen05.mma cta_group::1, M = 128, K = 16 per
-//        instruction, issued by one thread); epilogue tcgen05.ld -> bias / ReLU -> fp32 store.
+//        (CTA column group, k-chunk of 64): Wp[ng][kc][part][sub][BN rows][64 k] bf16 (swizzled,
+//        zero padded), so a block arrives with ONE cp.async.bulk (TMA engine) on an mbarrier.
+//   D  : n_sub accumulators of 128 x BN fp32 in TMEM (tcgen05.mma cta_group::1, M = 128, K = 16
+//        per instruction, single issuing thread).  bf16x3: D += Ahi*Whi + Alo*Whi + Ahi*Wlo.
+//   Pipeline: ring of up to 4 shared-memory stages; the MMAs of chunk c run asynchronously
+//        (tcgen05.commit -> mbarrier) while the CTA stages the following chunks.
+//   Epilogue: tcgen05.ld -> (+bias, ReLU) -> shared-memory tile -> warp-per-row coalesced stores,
+//        or, for the fused variant (CTA owns complete rows, N <= 320), + residual -> LayerNorm.
 //
-// One CTA = one 128-row x BN-column output tile; K is consumed in chunks of KC <= 288 that are
-// staged whole (A chunk <= 72 KB, W chunk <= 90 KB).  Replaces cuBLAS / cuDNN-1x1-conv call
-// sites of the reference in the bf16 mode (BASELINE.json configs[1]).
+// Replaces the cuBLAS / cuDNN-1x1-conv + BN + ReLU / LayerNorm call sites of the reference.
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 256;
+constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_ITEMS = 4;  // staged items (8 consecutive k of one row) per thread and k-chunk
+constexpr int KC = tc::KB;   // k-chunk = one 64-element swizzle block
+constexpr uint32_t A_PART = TC_BM * KC * 2;  // 16 KB
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-linear_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ A2, int lda2,
-                 const __nv_bfloat16 *__restrict__ Wp, const float *__restrict__ bias, float *__restrict__ Y, int ldy,
-                 int M, int N, int K, int KC, int n_chunks, int BN, int relu, int split) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bar_w, bar_mma;
+struct LinearTcParams {
+  const float *A, *A2, *bias, *R, *gamma, *beta;
+  const __nv_bfloat16 *Wp;
+  float *Y;
+  int lda, lda2, ldy, ldr;
+  int M, N, K, n_chunks, BN, n_sub, relu, split, n_stages;
+  float eps;
+  long long *dbg;  // optional clock64() stamps of CTA (0,0), thread 0 (tuning aid)
+};
+
+#define TC_STAMP(i)                                                                               \
+  do {                                                                                            \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[i] = clock64();    \
+  } while (0)
+
+template <bool LN_EPI, bool HAS_A2>
+__global__ void __launch_bounds__(TC_THREADS, HAS_A2 ? 1 : 2) linear_tc_kernel(const LinearTcParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // swizzle-128B tiles need 1024-byte aligned bases (in the shared address space)
+  unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) unsigned long long bar_w[TC_MAX_STAGES], bar_mma[TC_MAX_STAGES];
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // provably warp-uniform
+  TC_STAMP(0);
   const int row0 = blockIdx.x * TC_BM;
-  const int nt = blockIdx.y;
-  // split == 3: every fp32 operand x is carried as bf16 hi + bf16 lo (x ~ hi + lo to 16 mantissa
-  // bits) and D += Ahi*Whi + Alo*Whi + Ahi*Wlo, i.e. fp32-grade products at 3 MMAs per k-step.
-  const uint32_t parts = split == 3 ? 2u : 1u;
-  const uint32_t a_part = TC_BM * KC * 2, w_part = static_cast<uint32_t>(BN) * KC * 2;
-  const uint32_t a_bytes = a_part * parts, w_bytes = w_part * parts;
-  unsigned char *sA = smem;
-  unsigned char *sW = smem + a_bytes;
-  const uint32_t sbo = (KC / 8) * 128;
-  const uint32_t ncols = tc::tmem_cols_pow2(BN);
+  const int ng = blockIdx.y;  // column group: n_sub consecutive BN-wide tiles
+  const int BN = p.BN, n_sub = p.n_sub;
+  const uint32_t parts = p.split == 3 ? 2u : 1u;
+  const uint32_t w_blk = static_cast<uint32_t>(BN) * KC * 2;  // multiple of 1024 (BN % 8 == 0)
+  const uint32_t a_bytes = A_PART * parts, w_bytes = w_blk * parts * n_sub;
+  const uint32_t stage_bytes = a_bytes + w_bytes;
+  const uint32_t ncols = tc::tmem_cols_pow2(n_sub * BN);
 
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), ncols);
   if (tid == 32) {
-    tc::mbar_init(tc::smem_u32(&bar_w), 1);
-    tc::mbar_init(tc::smem_u32(&bar_mma), 1);
+    for (int i = 0; i < TC_MAX_STAGES; ++i) {
+      tc::mbar_init(tc::smem_u32(&bar_w[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_mma[i]), 1);
+    }
     tc::fence_mbar_init();
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
+  TC_STAMP(1);
+  const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
   const uint32_t idesc = tc::idesc_bf16(TC_BM, BN);
-  const int chunks_per_row = KC / 8;
+  __shared__ float bias_s[512];
 
-  for (int c = 0; c < n_chunks; ++c) {
-    if (c > 0) tc::mbar_wait(tc::smem_u32(&bar_mma), (c - 1) & 1);  // previous chunk's MMAs have read smem
-    if (tid == 0) {
-      tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_w), w_bytes);
-      tc::bulk_g2s(tc::smem_u32(sW), Wp + (static_cast<size_t>(nt) * n_chunks + c) * BN * KC * parts, w_bytes,
-                   tc::smem_u32(&bar_w));
-    }
-    // stage A: each thread converts 8 consecutive k of one row (32 B in, 16 B out).  Lanes are
-    // mapped (row % 8 fastest, then 4 adjacent k-chunks) so a warp writes 512 contiguous bytes.
-    const int k_base = c * KC;
-    const int n_quads = (chunks_per_row + 3) / 4;
-    for (int e = tid; e < TC_BM / 8 * n_quads * 32; e += TC_THREADS) {
-      const int l = e & 31, blk = e >> 5;
-      const int rg = blk / n_quads, q = blk % n_quads;
-      const int r = rg * 8 + (l & 7), ch = q * 4 + (l >> 3);
-      if (ch >= chunks_per_row) continue;
-      const int gr = row0 + r, gk = k_base + ch * 8;
-      float v[8];
+  // Per-thread staging plan, identical for every k-chunk.  A warp-item covers 8 rows x 4 chunks
+  // (lane = chunk_local * 8 + row_local): 128 contiguous bytes per row from global memory and
+  // conflict-free 16-byte st.shared into the swizzled tile.
+  long long g_off[TC_ITEMS], g2_off[TC_ITEMS];
+  uint32_t s_off[TC_ITEMS];
+  int k_off[TC_ITEMS];
+  bool row_ok[TC_ITEMS];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (gr < M && gk < K) {
-        const float *src = A + static_cast<long long>(gr) * lda + gk;
-        const float *src2 = A2 ? A2 + static_cast<long long>(gr) * lda2 + gk : nullptr;
-        if (gk + 8 <= K && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
-            (!src2 || (reinterpret_cast<uintptr_t>(src2) & 15) == 0)) {
-          const float4 a = *reinterpret_cast<const float4 *>(src), b = *reinterpret_cast<const float4 *>(src + 4);
-          v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
-          if (src2) {
-            const float4 p = *reinterpret_cast<const float4 *>(src2), q2 = *reinterpret_cast<const float4 *>(src2 + 4);
-            v[0] += p.x, v[1] += p.y, v[2] += p.z, v[3] += p.w, v[4] += q2.x, v[5] += q2.y, v[6] += q2.z, v[7] += q2.w;
-          }
-        } else {
+  for (int it = 0; it < TC_ITEMS; ++it) {
+    const int blk = warp + it * TC_WARPS;  // 0..31
+    const int r = (blk >> 1) * 8 + (lane & 7), ch = (blk & 1) * 4 + (lane >> 3);
+    row_ok[it] = row0 + r < p.M;
+    k_off[it] = ch * 8;
+    s_off[it] = tc::sw128_off(r, ch);
+    g_off[it] = static_cast<long long>(row0 + r) * p.lda + ch * 8;
+    g2_off[it] = static_cast<long long>(row0 + r) * p.lda2 + ch * 8;
+  }
+  float4 ra0[TC_ITEMS][2], rb0[TC_ITEMS][2], ra1[TC_ITEMS][2], rb1[TC_ITEMS][2];
+  auto issue_loads = [&](int c, float4 (&ra)[TC_ITEMS][2], float4 (&rb)[TC_ITEMS][2]) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (gk + i < K) v[i] = src[i] + (src2 ? src2[i] : 0.f);
-        }
-      }
-      uint4 pk;
-      pk.x = tc::pack_bf16x2(v[0], v[1]), pk.y = tc::pack_bf16x2(v[2], v[3]);
-      pk.z = tc::pack_bf16x2(v[4], v[5]), pk.w = tc::pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4 *>(sA + tc::canon_off(r, ch, sbo)) = pk;
-      if (parts == 2) {
-        float lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
-        pk.x = tc::pack_bf16x2(lo[0], lo[1]), pk.y = tc::pack_bf16x2(lo[2], lo[3]);
-        pk.z = tc::pack_bf16x2(lo[4], lo[5]), pk.w = tc::pack_bf16x2(lo[6], lo[7]);
-        *reinterpret_cast<uint4 *>(sA + a_part + tc::canon_off(r, ch, sbo)) = pk;
+    for (int it = 0; it < TC_ITEMS; ++it) {
+      const bool ok = row_ok[it] && (c * KC + k_off[it] < p.K);  // K % 8 == 0: whole item in range
+      const float4 *src = reinterpret_cast<const float4 *>(p.A + (ok ? g_off[it] + c * KC : 0));
+      ra[it][0] = __ldg(src), ra[it][1] = __ldg(src + 1);
+      if (HAS_A2) {
+        const float4 *src2 = reinterpret_cast<const float4 *>(p.A2 + (ok ? g2_off[it] + c * KC : 0));
+        rb[it][0] = __ldg(src2), rb[it][1] = __ldg(src2 + 1);
       }
     }
+  };
+
+  // S-stage ring.  W(c) is requested `S - lag` chunks ahead: at iteration c the stage last used by
+  // chunk c - lag is refilled (after its MMAs retired) with W(c - lag + S); lag = 2 when S >= 3 so
+  // that the barrier waited on belongs to MMAs issued a full iteration earlier.
+  const int S = p.n_stages;
+  const int lag = S >= 3 ? 2 : 1;
+  auto issue_w = [&](int c) {  // thread 0 only
+    const int st = c % S;
+    tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_w[st]), w_bytes);
+    tc::bulk_g2s(tc::smem_u32(smem + st * stage_bytes + a_bytes),
+                 p.Wp + (static_cast<size_t>(ng) * p.n_chunks + c) * (w_bytes / 2), w_bytes, tc::smem_u32(&bar_w[st]));
+  };
+  if (tid == 0)
+    for (int c = 0; c < S && c < p.n_chunks; ++c) issue_w(c);
+  issue_loads(0, ra0, rb0);
+  if (p.n_chunks > 1) issue_loads(1, ra1, rb1);
+  // bias -> shared memory (after the operand loads are in flight; the epilogue must not wait on global memory)
+  for (int i = tid; i < n_sub * BN; i += TC_THREADS) {
+    const int col = ng * n_sub * BN + i;
+    bias_s[i] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+  }
+  TC_STAMP(2);
+
+  auto step = [&](int c, float4 (&ra)[TC_ITEMS][2], float4 (&rb)[TC_ITEMS][2]) {
+    const int st = c % S;
+    unsigned char *sA = smem + st * stage_bytes;
+    // ---- convert + store chunk c (loads issued two iterations ago; the stage's previous MMAs,
+    //      chunk c - S, were observed complete by every thread at iteration c - S + lag)
+#pragma unroll
+    for (int it = 0; it < TC_ITEMS; ++it) {
+      const bool ok = row_ok[it] && (c * KC + k_off[it] < p.K);
+      float v[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w, ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
+      if (HAS_A2) {
+        v[0] += rb[it][0].x, v[1] += rb[it][0].y, v[2] += rb[it][0].z, v[3] += rb[it][0].w;
+        v[4] += rb[it][1].x, v[5] += rb[it][1].y, v[6] += rb[it][1].z, v[7] += rb[it][1].w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.f;
+      uint4 hi, lo;
+      tc::split_bf16x8(v, hi, lo);
+      *reinterpret_cast<uint4 *>(sA + s_off[it]) = hi;
+      if (parts == 2) *reinterpret_cast<uint4 *>(sA + A_PART + s_off[it]) = lo;
+    }
+    TC_STAMP(4 + 4 * c);
+    if (c + 2 < p.n_chunks) issue_loads(c + 2, ra, rb);  // refill this register set
+    if (c >= lag) {                                       // retire MMA(c - lag), refill its stage
+      const int j = c - lag;
+      tc::mbar_wait(tc::smem_u32(&bar_mma[j % S]), (j / S) & 1);
+      if (tid == 0 && j + S < p.n_chunks) issue_w(j + S);
+    }
+    TC_STAMP(5 + 4 * c);
     tc::fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
-      tc::mbar_wait(tc::smem_u32(&bar_w), c & 1);
+    TC_STAMP(6 + 4 * c);
+    if (warp == 0) {  // warp-uniform branch; one elected lane issues
+      tc::mbar_wait(tc::smem_u32(&bar_w[st]), (c / S) & 1);
       tc::fence_after_sync();
-      const uint32_t a0 = tc::smem_u32(sA), w0 = tc::smem_u32(sW);
+      if (tc::elect_one()) {
+      const uint32_t a0 = tc::smem_u32(sA), w0 = a0 + a_bytes;
+#pragma unroll
       for (int s = 0; s < KC / 16; ++s) {
-        const uint64_t da = tc::smem_desc(a0 + s * 256, 128, sbo);
-        const uint64_t db = tc::smem_desc(w0 + s * 256, 128, sbo);
-        tc::mma_bf16(tmem, da, db, idesc, (c > 0 || s > 0) ? 1u : 0u);
-        if (parts == 2) {
-          tc::mma_bf16(tmem, tc::smem_desc(a0 + a_part + s * 256, 128, sbo), db, idesc, 1u);
-          tc::mma_bf16(tmem, da, tc::smem_desc(w0 + w_part + s * 256, 128, sbo), idesc, 1u);
+        const uint64_t da_hi = tc::smem_desc_sw128(a0 + s * 32);
+        const uint64_t da_lo = tc::smem_desc_sw128(a0 + A_PART + s * 32);
+        const uint32_t acc = (c > 0 || s > 0) ? 1u : 0u;
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const uint32_t d = tmem + sub * BN;
+          const uint64_t dw_hi = tc::smem_desc_sw128(w0 + sub * w_blk + s * 32);
+          tc::mma_bf16(d, da_hi, dw_hi, idesc, acc);
+          if (parts == 2) {
+            const uint64_t dw_lo = tc::smem_desc_sw128(w0 + (n_sub + sub) * w_blk + s * 32);
+            tc::mma_bf16(d, da_lo, dw_hi, idesc, 1u);
+            tc::mma_bf16(d, da_hi, dw_lo, idesc, 1u);
+          }
         }
       }
-      tc::mma_commit(tc::smem_u32(&bar_mma));
+      tc::mma_commit(tc::smem_u32(&bar_mma[st]));
+      }
+      __syncwarp();
     }
+    TC_STAMP(7 + 4 * c);
+  };
+  for (int c = 0; c < p.n_chunks; c += 2) {
+    step(c, ra0, rb0);
+    if (c + 1 < p.n_chunks) step(c + 1, ra1, rb1);
   }
-  tc::mbar_wait(tc::smem_u32(&bar_mma), (n_chunks - 1) & 1);
+  // all MMAs retire in order: the last commit covers every earlier one
+  {
+    const int last = p.n_chunks - 1;
+    tc::mbar_wait(tc::smem_u32(&bar_mma[last % S]), (last / S) & 1);
+  }
   tc::fence_after_sync();
+  TC_STAMP(40);
 
-  // epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (its rows); the two warpgroups split the columns
-  const int r = (warp & 3) * 32 + lane;
-  const int gr = row0 + r;
-  const int half = (BN / 16 + 1) / 2;  // 16-column groups per warpgroup
-  const int g0 = (warp >> 2) * half, g1 = min(BN / 16, g0 + half);
-  for (int g = g0; g < g1; ++g) {
-    uint32_t acc[16];
-    tc::tmem_ld16(tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * 16, acc);
-    tc::tmem_ld_wait();
-    if (gr < M) {
-      const int col0 = nt * BN + g * 16;
-      float *dst = Y + static_cast<long long>(gr) * ldy + col0;
+  // ---- epilogue 1: TMEM -> (+bias, ReLU) -> shared tile (row stride NC + 4 floats).
+  // warp w owns TMEM lanes 32*(w%4)..+31; the warpgroups split the 16-column groups.
+  const int NC = n_sub * BN;
+  const int ldt = NC + 4;
+  float *tile = reinterpret_cast<float *>(smem);
+  const int col_base = ng * NC;
+  {
+    const int r = (warp & 3) * 32 + lane;
+    const int n_groups = NC / 16;
+    constexpr int WG = TC_THREADS / 128;
+    const int per = (n_groups + WG - 1) / WG;
+    const int g0 = (warp >> 2) * per, g1 = min(n_groups, g0 + per);
+    const uint32_t tbase = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int g = g0; g < g1; g += 2) {
+      uint32_t acc[2][16];
+      tc::tmem_ld16(tbase + g * 16, acc[0]);
+      if (g + 1 < g1) tc::tmem_ld16(tbase + (g + 1) * 16, acc[1]);
+      tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = col0 + j;
-        if (col < N) {
-          float v = __uint_as_float(acc[j]) + (bias ? __ldg(bias + col) : 0.f);
-          if (relu) v = fmaxf(v, 0.f);
-          dst[j] = v;
+      for (int u = 0; u < 2; ++u) {
+        if (g + u >= g1) break;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = __uint_as_float(acc[u][j]) + bias_s[(g + u) * 16 + j];
+          if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
+          o[j] = v;
         }
+        float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + (g + u) * 16);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+        dst[3] = make_float4(o[12], o[13], o[14], o[15]);
       }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+  TC_STAMP(41);
+
+  // ---- epilogue 2: warp-per-row coalesced write-out
+  const int n_valid = min(NC, p.N - col_base);
+  if (!LN_EPI) {
+    const bool vec = (p.ldy % 4 == 0) && (n_valid % 4 == 0) && (col_base % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
+    if (vec) {
+      const int f4 = n_valid / 4;
+#pragma unroll 4
+      for (int i = 0; i < TC_BM / TC_WARPS; ++i) {
+        const int r = warp + i * TC_WARPS, gr = row0 + r;
+        if (gr < p.M) {
+          float4 *y = reinterpret_cast<float4 *>(p.Y + static_cast<long long>(gr) * p.ldy + col_base);
+          const float4 *t = reinterpret_cast<const float4 *>(tile + r * ldt);
+          if (lane < f4) y[lane] = t[lane];
+          if (lane + 32 < f4) y[lane + 32] = t[lane + 32];
+          for (int q = lane + 64; q < f4; q += 32) y[q] = t[q];
+        }
+      }
+    } else {
+      for (int r = warp; r < TC_BM; r += TC_WARPS) {
+        const int gr = row0 + r;
+        if (gr >= p.M) break;
+        float *y = p.Y + static_cast<long long>(gr) * p.ldy + col_base;
+        const float *t = tile + r * ldt;
+        for (int q = lane; q < n_valid; q += 32) y[q] = t[q];
+      }
+    }
+  } else {
+    // LayerNorm(tile + residual): one warp per row, 4 rows per round so that the residual loads of
+    // a round (40 per lane) are all in flight together.  N <= 320: 10 columns per lane.
+    const float inv_n = 1.0f / static_cast<float>(p.N);
+    float gam[10], bet[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int col = lane + i * 32;
+      gam[i] = col < p.N ? __ldg(p.gamma + col) : 0.f;
+      bet[i] = col < p.N ? __ldg(p.beta + col) : 0.f;
+    }
+    for (int r0 = warp; r0 < TC_BM; r0 += TC_WARPS * 4) {
+      float x[4][10];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * TC_WARPS, gr = row0 + r;
+        const bool rok = r < TC_BM && gr < p.M;
+        const float *res = p.R + (rok ? static_cast<long long>(gr) * p.ldr : 0);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int col = lane + i * 32;
+          x[u][i] = (rok && col < p.N) ? __ldg(res + col) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * TC_WARPS, gr = row0 + r;
+        if (r >= TC_BM || gr >= p.M) continue;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int col = lane + i * 32;
+          if (col < p.N) x[u][i] += tile[r * ldt + col];
+          sum += x[u][i];
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+        const float mean = sum * inv_n;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int col = lane + i * 32;
+          const float d = col < p.N ? x[u][i] - mean : 0.f;
+          sq = fmaf(d, d, sq);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
+        const float rstd = rsqrtf(sq * inv_n + p.eps);
+        float *y = p.Y + static_cast<long long>(gr) * p.ldy;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int col = lane + i * 32;
+          if (col < p.N) y[col] = (x[u][i] - mean) * rstd * gam[i] + bet[i];
+        }
+      }
+    }
+  }
+  TC_STAMP(42);
 }
+
+int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
+  const int NC = p.n_sub * p.BN;
+  const uint32_t parts = p.split == 3 ? 2 : 1;
+  const size_t stage = static_cast<size_t>(parts) * (TC_BM + NC) * KC * 2;
+  int stages = static_cast<int>((220 * 1024) / stage);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > p.n_chunks) stages = p.n_chunks;
+  BD_REQUIRE(stages >= 1 && (stages >= 2 || p.n_chunks == 1),
+             "bd_linear_tc: a pipeline stage needs %zu bytes of shared memory; two must fit 220 KB", stage);
+  p.n_stages = stages;
+  const size_t pipe = stage * stages;
+  const size_t tile = static_cast<size_t>(TC_BM) * (NC + 4) * 4;
+  const size_t smem = (pipe > tile ? pipe : tile) + 1024;  // slack: the dynamic base is 1024-aligned by hand
+  BD_REQUIRE(smem <= 224 * 1024, "bd_linear_tc: tiling needs %zu bytes of shared memory (> 224 KB)", smem);
+  static thread_local bool configured = false;
+  if (!configured) {
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    configured = true;
+  }
+  const int n_groups = bd::ceil_div(p.N, NC);
+  BD_REQUIRE(n_groups <= 65535, "bd_linear_tc: N too large");
+  dim3 grid(bd::ceil_div(p.M, TC_BM), n_groups);
+  if (ln && p.A2)
+    linear_tc_kernel<true, true><<<grid, TC_THREADS, smem, stream>>>(p);
+  else if (ln)
+    linear_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(p);
+  else if (p.A2)
+    linear_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(p);
+  else
+    linear_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(p);
+  return BD_OK;
+}
+
+int check_common(const float *A, const void *Wp, float *Y, int lda, int A2_ok, int ldy, int M, int N, int K,
+                 int kc, int n_chunks, int BN, int n_sub, int split) {
+  BD_REQUIRE(A && Wp && Y, "bd_linear_tc: null pointer");
+  BD_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldy >= N && A2_ok, "bd_linear_tc: bad sizes");
+  BD_REQUIRE(kc == KC && n_chunks >= 1 && n_chunks * KC >= K, "bd_linear_tc: KC must be 64 and n_chunks * 64 >= K");
+  BD_REQUIRE(K % 8 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0,
+             "bd_linear_tc: needs K %% 8 == 0, lda %% 4 == 0 and a 16-byte aligned A (use bd_linear_f32 otherwise)");
+  BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "bd_linear_tc: BN must be a multiple of 16 in [16,256]");
+  BD_REQUIRE(n_sub >= 1 && n_sub * BN <= 512, "bd_linear_tc: n_sub * BN must fit 512 TMEM columns");
+  BD_REQUIRE(split == 1 || split == 3, "bd_linear_tc: split must be 1 (bf16) or 3 (bf16x3)");
+  return BD_OK;
+}
+
+long long *g_tc_dbg = nullptr;
 
 }  // namespace
 
+// Tuning aid: device buffer of >= 64 long longs receiving clock64() stamps of CTA (0,0); NULL disables.
+extern "C" int bd_linear_tc_set_debug(long long *buf) {
+  g_tc_dbg = buf;
+  return BD_OK;
+}
+
 extern "C" int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp, const float *bias,
-                            float *Y, int ldy, int M, int N, int K, int KC, int n_chunks, int BN, int relu,
-                            int split, bd_stream_t stream) {
-  BD_REQUIRE(A && Wp && Y, "bd_linear_tc: null pointer");
-  BD_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldy >= N && (!A2 || lda2 >= K), "bd_linear_tc: bad sizes");
-  BD_REQUIRE(KC % 16 == 0 && KC >= 16 && KC <= 288 && n_chunks >= 1 && n_chunks * KC >= K,
-             "bd_linear_tc: KC must be a multiple of 16 in [16,288] covering K");
-  BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "bd_linear_tc: BN must be a multiple of 16 in [16,256]");
-  const int n_tiles = bd::ceil_div(N, BN);
-  BD_REQUIRE(n_tiles <= 65535, "bd_linear_tc: N too large");
-  BD_REQUIRE(split == 1 || split == 3, "bd_linear_tc: split must be 1 (bf16) or 3 (bf16x3)");
-  const size_t smem = static_cast<size_t>(TC_BM + BN) * KC * 2 * (split == 3 ? 2 : 1);
-  BD_REQUIRE(smem <= 226 * 1024, "bd_linear_tc: tile does not fit shared memory");
-  static thread_local bool configured = false;
-  if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
-            "bd_linear_tc");
-    configured = true;
-  }
-  dim3 grid(bd::ceil_div(M, TC_BM), n_tiles);
-  linear_tc_kernel<<<grid, TC_THREADS, smem, bd::as_stream(stream)>>>(
-      A, lda, A2, lda2, static_cast<const __nv_bfloat16 *>(Wp), bias, Y, ldy, M, N, K, KC, n_chunks, BN, relu, split);
+                            float *Y, int ldy, int M, int N, int K, int kc, int n_chunks, int BN, int n_sub,
+                            int relu, int split, bd_stream_t stream) {
+  const int rc = check_common(A, Wp, Y, lda,
+                              !A2 || (lda2 >= K && lda2 % 4 == 0 && (reinterpret_cast<uintptr_t>(A2) & 15) == 0), ldy,
+                              M, N, K, kc, n_chunks, BN, n_sub, split);
+  if (rc != BD_OK) return rc;
+  LinearTcParams p = {};
+  p.A = A, p.A2 = A2, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y;
+  p.lda = lda, p.lda2 = lda2, p.ldy = ldy;
+  p.M = M, p.N = N, p.K = K, p.n_chunks = n_chunks, p.BN = BN, p.n_sub = n_sub, p.relu = relu, p.split = split;
+  p.dbg = g_tc_dbg;
+  const int r2 = launch_linear_tc(p, false, bd::as_stream(stream));
+  if (r2 != BD_OK) return r2;
   BD_CHECK_LAUNCH("bd_linear_tc");
+  return BD_OK;
+}
+
+extern "C" int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp, const float *bias,
+                               const float *R, int ldr, const float *gamma, const float *beta, float eps, float *Y,
+                               int ldy, int M, int N, int K, int kc, int n_chunks, int BN, int n_sub, int split,
+                               bd_stream_t stream) {
+  const int rc = check_common(A, Wp, Y, lda,
+                              !A2 || (lda2 >= K && lda2 % 4 == 0 && (reinterpret_cast<uintptr_t>(A2) & 15) == 0), ldy,
+                              M, N, K, kc, n_chunks, BN, n_sub, split);
+  if (rc != BD_OK) return rc;
+  BD_REQUIRE(R && gamma && beta && ldr >= N, "bd_linear_ln_tc: null pointer / bad ldr");
+  BD_REQUIRE(n_sub * BN >= N && N <= 320, "bd_linear_ln_tc: one CTA must own complete rows (N <= n_sub*BN, N <= 320)");
+  LinearTcParams p = {};
+  p.A = A, p.A2 = A2, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y;
+  p.R = R, p.gamma = gamma, p.beta = beta, p.eps = eps, p.ldr = ldr;
+  p.lda = lda, p.lda2 = lda2, p.ldy = ldy;
+  p.M = M, p.N = N, p.K = K, p.n_chunks = n_chunks, p.BN = BN, p.n_sub = n_sub, p.relu = 0, p.split = split;
+  p.dbg = g_tc_dbg;
+  const int r2 = launch_linear_tc(p, true, bd::as_stream(stream));
+  if (r2 != BD_OK) return r2;
+  BD_CHECK_LAUNCH("bd_linear_ln_tc");
   return BD_OK;
 }

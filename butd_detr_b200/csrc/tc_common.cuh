@@ -1,13 +1,17 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy primitives (inline PTX) shared by the tensor-core kernels.
 // sm_100a only.  Layout conventions used by every tensor-core kernel in this library:
 //
-//   * operands are K-MAJOR and stored in shared memory in the canonical NO-SWIZZLE core-matrix
-//     layout: a core matrix is 8 rows x 16 bytes (8 bf16 along K), 128 contiguous bytes;
-//     core matrices along K are adjacent (LBO = 128 B), 8-row groups along M/N are
-//     SBO = (KC / 8) * 128 B apart, KC = K extent of the staged tile:
-//         byte(row r, k) = (r / 8) * SBO + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2
-//     This is the layout threads can write directly with 16-byte st.shared (gathered rows,
-//     softmax probabilities, MLP activations) and that pre-packed weights are bulk-copied into.
+//   * operands are K-MAJOR bf16, staged in shared memory in the canonical 128-BYTE-SWIZZLE layout
+//     (UMMA LayoutType::SWIZZLE_128B, the layout TMA's CU_TENSOR_MAP_SWIZZLE_128B produces): a tile
+//     of R rows is cut along K into blocks of 64 elements (128 bytes per row); inside a block
+//         byte(row r, k) = (r / 8) * 1024 + (r % 8) * 128 + (((k / 8) ^ (r % 8)) * 16) + (k % 8) * 2
+//     i.e. 8-row groups of 1024 bytes whose 16-byte chunks are XOR-swizzled with the row number —
+//     conflict-free both for 16-byte st.shared from threads (gathered rows, softmax probabilities,
+//     MLP activations) and for the tensor core's operand fetch.  Block b of a tile starts at
+//     b * R * 128 bytes; every block base is 1024-byte aligned.  (A first version used the
+//     un-swizzled core-matrix layout: correct, but each MMA then took ~4x its nominal cycles.)
+//   * weights are pre-packed by the host in exactly this layout, so a block arrives with one
+//     cp.async.bulk (TMA engine) signalled on an mbarrier.
 //   * accumulators live in TMEM: D[row i][col j] = lane i, column base + j (cta_group::1, M=128).
 #pragma once
 #include <cuda_bf16.h>
@@ -16,8 +20,18 @@
 
 namespace tc {
 
+constexpr int KB = 64;  // K elements per swizzle block (128 bytes of bf16)
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// one elected lane of a fully converged warp (the CUTLASS pattern that lets the compiler keep
+// MMA descriptors in uniform registers instead of emitting per-lane R2UR loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- mbarrier
@@ -67,7 +81,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t tmem_cols_pow2(uint32_t n) {
+__host__ __device__ inline uint32_t tmem_cols_pow2(uint32_t n) {
   uint32_t c = 32;
   while (c < n) c <<= 1;
   return c;
@@ -84,14 +98,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type 0
-__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1),
+// [32,46) SBO>>4 = 1024 B between 8-row groups, [46,48) version = 1, [61,64) layout type = 2.
+// Advancing along K inside a 64-element block = adding the byte offset (32 B per 16 elements)
+// to the start address; the hardware applies the XOR swizzle on the final address bits.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= 1ull << 46;
+  d |= 2ull << 61;
   return d;
 }
 // instruction descriptor, kind::f16, A/B = bf16 K-major, D = f32 (cute::UMMA::InstrDescriptor)
@@ -112,14 +130,25 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// byte offset of (row r, 8-element k-chunk c) in a canonical tile with KC/8 = chunks per row group
-__device__ __forceinline__ uint32_t canon_off(uint32_t r, uint32_t c, uint32_t sbo_bytes) {
-  return (r >> 3) * sbo_bytes + c * 128u + (r & 7u) * 16u;
+// byte offset of (row r, 16-byte chunk c in 0..7) inside one 64-wide swizzle block
+__device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((c ^ (r & 7u)) << 4);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// 8 fp32 -> 8 bf16 (hi) and, optionally, the 8 bf16 residuals (lo) of the bf16x3 split
+__device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+  hi.x = pack_bf16x2(v[0], v[1]), hi.y = pack_bf16x2(v[2], v[3]);
+  hi.z = pack_bf16x2(v[4], v[5]), hi.w = pack_bf16x2(v[6], v[7]);
+  lo.x = pack_bf16x2(r[0], r[1]), lo.y = pack_bf16x2(r[2], r[3]);
+  lo.z = pack_bf16x2(r[4], r[5]), lo.w = pack_bf16x2(r[6], r[7]);
 }
 
 }  // namespace tc

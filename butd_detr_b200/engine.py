@@ -57,32 +57,40 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
-def tc_tiling(N, K, split=1):
-    """(BN, KC, n_chunks) used by bd_linear_tc for an (N, K) weight: BN <= 160 columns per CTA
-    (multiple of 16), K consumed in equal chunks of KC (multiple of 16) <= 288 (split 1) or
-    <= 144 (split 3: hi and lo parts of both operands are staged)."""
+TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
+
+
+def tc_tiling(N, K, split=1, full_rows=False):
+    """(BN, KC, n_chunks, n_sub) for bd_linear_tc / bd_linear_ln_tc on an (N, K) weight.
+    BN <= 160 columns per accumulator (multiple of 16); a CTA computes n_sub of them (all of
+    them when `full_rows`, so that the LayerNorm epilogue sees complete rows); K is consumed in
+    chunks of 64 (one 128-byte-swizzle block), zero padded."""
     nt = -(-N // 160)
     BN = _round_up(-(-N // nt), 16)
-    kc_max = 288 if split == 1 else 144
-    n_chunks = -(-K // kc_max)
-    KC = _round_up(-(-K // n_chunks), 16)
-    return BN, KC, n_chunks
+    n_sub = nt if full_rows else 1
+    n_chunks = -(-K // TC_KC)
+    return BN, TC_KC, n_chunks, n_sub
 
 
-def pack_weight_tc(W, split=1):
-    """(N, K) fp32 -> bf16 blocks in the tensor-core kernels' shared-memory layout
-    Wp[n_tile][k_chunk][part][BN/8][KC/8][8 rows][8 k] (see csrc/tc_common.cuh), zero padded;
-    part = {hi} or, for split 3, {hi, lo} with lo = bf16(W - hi)."""
+def pack_weight_tc(W, split=1, full_rows=False):
+    """(N, K) fp32 -> bf16 blocks in the tensor-core kernels' shared-memory layout (128-byte
+    swizzle, K-major; csrc/tc_common.cuh): Wp[n_group][k_chunk][part][sub][BN rows][64 k] where
+    the 16-byte chunk j of row r holds k-chunk (j ^ (r % 8)); zero padded; part = {hi} or, for
+    split 3, {hi, lo} with lo = bf16(W - hi)."""
     N, K = W.shape
-    BN, KC, n_chunks = tc_tiling(N, K, split)
-    nt = -(-N // BN)
-    Wp = W.new_zeros(nt * BN, n_chunks * KC)
+    BN, KC, n_chunks, n_sub = tc_tiling(N, K, split, full_rows)
+    ng = -(-N // (BN * n_sub))
+    Wp = W.new_zeros(ng * n_sub * BN, n_chunks * KC)
     Wp[:N, :K] = W
     hi = Wp.to(torch.bfloat16)
     parts = [hi] if split == 1 else [hi, (Wp - hi.float()).to(torch.bfloat16)]
-    P = torch.stack(parts, 0)  # (part, N_pad, K_pad)
-    P = P.view(len(parts), nt, BN // 8, 8, n_chunks, KC // 8, 8).permute(1, 4, 0, 2, 5, 3, 6)
-    return P.contiguous(), (BN, KC, n_chunks)
+    P = torch.stack(parts, 0).view(len(parts), ng, n_sub, BN, n_chunks, 8, 8)  # (..., row, kc, chunk, elem)
+    r = torch.arange(BN, device=W.device) % 8
+    src_chunk = torch.arange(8, device=W.device)[None, :] ^ r[:, None]         # (BN, 8): logical chunk at slot j
+    idx = src_chunk.view(1, 1, 1, BN, 1, 8, 1).expand(len(parts), ng, n_sub, BN, n_chunks, 8, 8)
+    P = torch.gather(P, 5, idx)
+    P = P.permute(1, 4, 0, 2, 3, 5, 6)  # (ng, kc, part, sub, row, chunk, elem)
+    return P.contiguous(), (BN, KC, n_chunks, n_sub)
 
 
 class PackedWeights:
@@ -96,7 +104,7 @@ class PackedWeights:
                 p = f"{bb}{name}.mlp_module.layer{i}"
                 W = sd[p + ".conv.weight"]
                 k = W.shape[1]
-                w[f"{name}.{i}"] = _fold_bn(W, None, sd, p + ".bn.bn", _round_up(k, 4) if i == 0 else None)
+                w[f"{name}.{i}"] = _fold_bn(W, None, sd, p + ".bn.bn", _round_up(k, 8) if i == 0 else None)
         for name in ("fp1", "fp2"):
             for i in range(2):
                 p = f"{bb}{name}.mlp.layer{i}"
@@ -219,15 +227,37 @@ class ForwardEngine:
             out = self._empty(M, N)
         assert out.stride(1) == 1
         lda2 = 0 if add is None else add.stride(0)
-        if self.precision != "fp32" and N >= 16:  # tensor cores; the 1-/3-wide heads stay on the fp32 kernel
+        tc_ok = (N >= 16 and K % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and
+                 (add is None or (add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0)))
+        if self.precision != "fp32" and tc_ok:  # tensor cores; 1-/3-wide heads and K = 3 / 6 inputs stay fp32
             if key not in self._tc:
                 self._tc[key] = pack_weight_tc(W, self.split)
-            Wp, (BN, KC, n_chunks) = self._tc[key]
+            Wp, (BN, KC, n_chunks, n_sub) = self._tc[key]
             _lib.call("bd_linear_tc", x.data_ptr(), x.stride(0), _lib.ptr(add), lda2, Wp.data_ptr(), _lib.ptr(b),
-                      out.data_ptr(), out.stride(0), M, N, K, KC, n_chunks, BN, int(relu), self.split)
+                      out.data_ptr(), out.stride(0), M, N, K, KC, n_chunks, BN, n_sub, int(relu), self.split)
         else:
             _lib.call("bd_linear_f32", x.data_ptr(), x.stride(0), _lib.ptr(add), lda2, W.data_ptr(), _lib.ptr(b),
                       out.data_ptr(), out.stride(0), M, N, K, int(relu))
+        return out
+
+    def lin_ln(self, x, key, res, ln_key, add=None, eps=LN_EPS):
+        """LayerNorm(res + linear(x [+ add])) — one kernel on the tensor-core path."""
+        W, b = self.W[key]
+        M, K = x.shape
+        N = W.shape[0]
+        if (self.precision == "fp32" or N > 320 or K % 8 or x.stride(0) % 4 or x.data_ptr() % 16 or
+                (add is not None and (add.stride(0) % 4 or add.data_ptr() % 16))):
+            return self.add_ln(self.lin(x, key, add=add), res, ln_key, eps)
+        assert x.stride(1) == 1 and W.shape[1] == K and res.is_contiguous() and res.shape == (M, N)
+        tkey = key + "#rows"
+        if tkey not in self._tc:
+            self._tc[tkey] = pack_weight_tc(W, self.split, full_rows=True)
+        Wp, (BN, KC, n_chunks, n_sub) = self._tc[tkey]
+        g, beta = self.W[ln_key]
+        out = self._empty(M, N)
+        _lib.call("bd_linear_ln_tc", x.data_ptr(), x.stride(0), _lib.ptr(add), 0 if add is None else add.stride(0),
+                  Wp.data_ptr(), _lib.ptr(b), res.data_ptr(), N, g.data_ptr(), beta.data_ptr(), float(eps),
+                  out.data_ptr(), N, M, N, K, KC, n_chunks, BN, n_sub, self.split)
         return out
 
     def add_ln(self, x, res, key, eps=LN_EPS, out=None):
@@ -250,9 +280,10 @@ class ForwardEngine:
                   Lq * E, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd))
         return out
 
-    def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False):
+    def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False, res=None, ln_key=None):
         """nn.MultiheadAttention (eval) incl. in/out projections.  q = x_q (+pos_q);
-        k = x_kv (+pos_k); v = x_kv.  Returns the out-projected (B*Lq, E) tensor."""
+        k = x_kv (+pos_k); v = x_kv.  Returns LayerNorm(res + out_proj(attention)) — the
+        post-LN residual block every call site of the reference wraps around the attention."""
         E = self.d_model
         if self_attn and pos_q is None:  # q = k = v = x : one fused QKV GEMM
             qkv = self.lin(x_q, key + ".qkv")
@@ -267,10 +298,11 @@ class ForwardEngine:
             kv = self.lin(x_kv, key + ".kv")
             k, v = kv[:, :E], kv[:, E:]
         o = self.attention(q, k, v, B, Lq, Lk, mask)
-        return self.lin(o, key + ".o")
+        return self.lin_ln(o, key + ".o", res, ln_key)
 
-    def ffn(self, x, key):
-        return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
+    def ffn(self, x, key, ln_key):
+        """LayerNorm(x + W2 relu(W1 x))  (encoder_decoder_layers.py:52-58,96,122)."""
+        return self.lin_ln(self.lin(x, key + ".0", relu=True), key + ".1", x, ln_key)
 
     def posembed(self, x, key):
         return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
@@ -466,19 +498,15 @@ class ForwardEngine:
             for i in range(cfg["num_encoder_layers"]):
                 k = f"enc{i}"
                 if cfg["self_attend"]:
-                    vis = self.add_ln(self.mha(k + ".sv", vis, pos, vis, pos, B, V, V, None, self_attn=True), vis, k + ".sv.ln")
-                    text = self.add_ln(self.mha(k + ".sl", text, None, text, None, B, L, L, tmask_u8, self_attn=True),
-                                       text, k + ".sl.ln")
+                    vis = self.mha(k + ".sv", vis, pos, vis, pos, B, V, V, None, True, vis, k + ".sv.ln")
+                    text = self.mha(k + ".sl", text, None, text, None, B, L, L, tmask_u8, True, text, k + ".sl.ln")
                 text_kv = text  # cross_vl attends to the text BEFORE the cross_lv update (:84)
-                t2 = self.mha(k + ".lv", text, None, vis, None, B, L, V, None)
-                text = self.add_ln(t2, text, k + ".norm_lv")
-                text = self.add_ln(self.ffn(text, k + ".ffn_lv"), text, k + ".norm_lv2")
-                v2 = self.mha(k + ".vl", vis, pos, text_kv, None, B, V, L, tmask_u8)
-                vis = self.add_ln(v2, vis, k + ".norm_vl")
+                text = self.mha(k + ".lv", text, None, vis, None, B, L, V, None, False, text, k + ".norm_lv")
+                text = self.ffn(text, k + ".ffn_lv", k + ".norm_lv2")
+                vis = self.mha(k + ".vl", vis, pos, text_kv, None, B, V, L, tmask_u8, False, vis, k + ".norm_vl")
                 if cfg["butd"]:
-                    v2 = self.mha(k + ".d", vis, None, det, None, B, V, D, dmask_u8)
-                    vis = self.add_ln(v2, vis, k + ".norm_d")
-                vis = self.add_ln(self.ffn(vis, k + ".ffn_vl"), vis, k + ".norm_vl2")
+                    vis = self.mha(k + ".d", vis, None, det, None, B, V, D, dmask_u8, False, vis, k + ".norm_d")
+                vis = self.ffn(vis, k + ".ffn_vl", k + ".norm_vl2")
             ep["text_memory"] = text.view(B, L, E)
             ep["seed_features"] = vis.view(B, V, E).transpose(1, 2)
             if cfg["contrastive_align_loss"]:
@@ -518,13 +546,12 @@ class ForwardEngine:
                 else:
                     qp_in = None
                 qpos = self.posembed(qp_in, k + ".posembed") if qp_in is not None else None
-                q2 = self.mha(k + ".self", query, qpos, query, qpos, B, Q, Q, None, self_attn=True)
-                query = self.add_ln(q2, query, k + ".norm1")
-                query = self.add_ln(self.mha(k + ".l", query, qpos, text, None, B, Q, L, tmask_u8), query, k + ".norm_l")
+                query = self.mha(k + ".self", query, qpos, query, qpos, B, Q, Q, None, True, query, k + ".norm1")
+                query = self.mha(k + ".l", query, qpos, text, None, B, Q, L, tmask_u8, False, query, k + ".norm_l")
                 if cfg["butd"]:
-                    query = self.add_ln(self.mha(k + ".d", query, qpos, det, None, B, Q, D, dmask_u8), query, k + ".norm_d")
-                query = self.add_ln(self.mha(k + ".v", query, qpos, vis, None, B, Q, V, None), query, k + ".norm_v")
-                query = self.add_ln(self.ffn(query, k + ".ffn"), query, k + ".norm2")
+                    query = self.mha(k + ".d", query, qpos, det, None, B, Q, D, dmask_u8, False, query, k + ".norm_d")
+                query = self.mha(k + ".v", query, qpos, vis, None, B, Q, V, None, False, query, k + ".norm_v")
+                query = self.ffn(query, k + ".ffn", k + ".norm2")
                 if cfg["contrastive_align_loss"]:
                     ep[prefix + "proj_queries"] = self.contrastive(query, "image", B, Q)
                 base_xyz, base_size = self.head(query, cluster_xyz, f"head{i}", ep, prefix, B, Q)

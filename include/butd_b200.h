@@ -131,15 +131,30 @@ int bd_linear_f32(const float *A, int lda, const float *A2, int lda2, const floa
 /* Same contract as bd_linear_f32, computed on the 5th-gen tensor cores (tcgen05.mma, bf16
  * operands, fp32 accumulation in TMEM).  A is converted to bf16 while it is staged; `Wp` is the
  * weight pre-packed by the host (butd_detr_b200.engine.pack_weight_tc) into the kernel's shared
- * memory layout:  Wp[n_tile][k_chunk][part][BN/8][KC/8][8 rows][8 k] bf16, zero padded, where
- * n_tile = n / BN, k_chunk = k / KC.  KC: multiple of 16, <= 288; BN: multiple of 16, <= 256.
+ * memory layout:  Wp[n_group][k_chunk][part][sub][BN/8][KC/8][8 rows][8 k] bf16, zero padded,
+ * where one CTA computes n_sub consecutive BN-wide column tiles (n_group = n / (n_sub*BN),
+ * sub = (n / BN) % n_sub) and k_chunk = k / KC.  KC: multiple of 16; BN: multiple of 16, <= 256;
+ * n_sub * BN <= 512 (TMEM columns).
  * split = 1: plain bf16 operands (part = {hi}).  split = 3 ("bf16x3"): every fp32 operand is
  * carried as bf16 hi + bf16 lo and D += Ahi*Whi + Alo*Whi + Ahi*Wlo (part = {hi, lo}), which
- * restores fp32-grade products on the bf16 tensor pipe.  (128 + BN) * KC * 2 * parts bytes must
- * fit 226 KB of shared memory. */
+ * restores fp32-grade products on the bf16 tensor pipe.  Two pipeline stages of
+ * parts * (128 + n_sub*BN) * KC * 2 bytes must fit 226 KB of shared memory. */
 int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp,
                  const float *bias, float *Y, int ldy, int M, int N, int K, int KC, int n_chunks,
-                 int BN, int relu, int split, bd_stream_t stream);
+                 int BN, int n_sub, int relu, int split, bd_stream_t stream);
+
+/* Tuning aid: device buffer (>= 64 x int64) that receives clock64() stamps of the phases of CTA
+ * (0,0) of every following bd_linear*_tc launch; NULL disables. */
+int bd_linear_tc_set_debug(long long *buf);
+
+/* Fused  Y = LayerNorm(R + (A [+ A2]) · Wᵀ + bias) * gamma + beta  on the same kernel: the CTA
+ * owns complete rows (n_sub * BN >= N, N <= 320), so the residual add and the row-wise
+ * LayerNorm run in the epilogue (post-LN blocks of encoder_decoder_layers.py: attention
+ * out-projection + norm, FFN second layer + norm). */
+int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp,
+                    const float *bias, const float *R, int ldr, const float *gamma,
+                    const float *beta, float eps, float *Y, int ldy, int M, int N, int K, int KC,
+                    int n_chunks, int BN, int n_sub, int split, bd_stream_t stream);
 
 /* Y[r,:] = LayerNorm(X[r,:] + R[r,:]) * gamma + beta   (R may be NULL), rows of D floats,
  * biased variance, eps inside the sqrt (torch.nn.LayerNorm). */

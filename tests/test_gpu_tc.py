@@ -16,7 +16,7 @@ def _g(seed):
 @pytest.mark.parametrize("M,N,K,relu,add", [(128, 64, 16, False, False), (128, 144, 288, False, False),
                                              (256, 288, 288, True, False), (1024, 576, 288, False, True),
                                              (80, 288, 288, False, False), (300, 256, 288, True, False),
-                                             (1000, 128, 132, True, False), (4099, 64, 8, True, False),
+                                             (1000, 128, 136, True, False), (4099, 64, 8, True, False),
                                              (513, 160, 768, False, False), (512, 256, 512, True, False),
                                              (200, 864, 288, False, False), (77, 64, 288, False, False)])
 @pytest.mark.parametrize("split", [1, 3])
@@ -27,10 +27,10 @@ def test_linear_tc(cuda_lib, M, N, K, relu, add, split):
     A2 = torch.randn(M, K, device="cuda", generator=g) if add else None
     W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
     b = torch.randn(N, device="cuda", generator=g)
-    Wp, (BN, KC, nch) = pack_weight_tc(W, split)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, split)
     Y = torch.full((M, N), float("nan"), device="cuda")
     cuda_lib.call("bd_linear_tc", A.data_ptr(), K, cuda_lib.ptr(A2), K, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), N,
-                  M, N, K, KC, nch, BN, int(relu), split)
+                  M, N, K, KC, nch, BN, nsub, int(relu), split)
     torch.cuda.synchronize()
     a = A + A2 if add else A
     if split == 1:  # plain bf16 operands: compare with the same rounding applied
@@ -48,11 +48,37 @@ def test_linear_tc_strided(cuda_lib):
     g = _g(9)
     big = torch.randn(300, 864, device="cuda", generator=g)
     W = torch.randn(160, 288, device="cuda", generator=g) / 17
-    Wp, (BN, KC, nch) = pack_weight_tc(W)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W)
     out = torch.zeros(300, 288, device="cuda")
     x = big[:, 288:576]
     cuda_lib.call("bd_linear_tc", x.data_ptr(), 864, None, 0, Wp.data_ptr(), None, out[:, 128:].data_ptr(), 288,
-                  300, 160, 288, KC, nch, BN, 0, 1)
+                  300, 160, 288, KC, nch, BN, nsub, 0, 1)
     want = (x.bfloat16().double() @ W.bfloat16().double().t()).float()
     torch.testing.assert_close(out[:, 128:], want, rtol=1e-4, atol=1e-4)
     assert float(out[:, :128].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("M,N,K,add", [(256, 288, 288, False), (1024, 288, 256, False), (80, 288, 288, True),
+                                        (130, 160, 64, False), (2048, 288, 288, False)])
+def test_linear_ln_tc(cuda_lib, M, N, K, add, split):
+    """Fused out-projection / FFN-2 + residual + LayerNorm epilogue."""
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(M * 3 + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    A2 = torch.randn(M, K, device="cuda", generator=g) if add else None
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g)
+    gam, bet = torch.rand(N, device="cuda", generator=g) + 0.5, torch.randn(N, device="cuda", generator=g)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, split, full_rows=True)
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    cuda_lib.call("bd_linear_ln_tc", A.data_ptr(), K, cuda_lib.ptr(A2), K, Wp.data_ptr(), b.data_ptr(), R.data_ptr(), N,
+                  gam.data_ptr(), bet.data_ptr(), 1e-5, Y.data_ptr(), N, M, N, K, KC, nch, BN, nsub, split)
+    a = A + A2 if add else A
+    if split == 1:
+        lin = F.linear(a.bfloat16().double(), W.bfloat16().double(), b.double())
+    else:
+        lin = F.linear(a.double(), W.double(), b.double())
+    want = F.layer_norm(R.double() + lin, (N,), gam.double(), bet.double(), 1e-5).float()
+    torch.testing.assert_close(Y, want, rtol=2e-4, atol=2e-4)

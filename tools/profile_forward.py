@@ -15,8 +15,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--points", type=int, default=50000)
+ap.add_argument("--precision", default="bf16x3")
 args = ap.parse_args()
-model = BeaUTyDETR(text_encoder=None)
+model = BeaUTyDETR(text_encoder=None, precision=args.precision)
 synth.fill_state_dict_(model.state_dict(), 0)
 model = model.cuda().eval()
 inputs = {k: v.cuda() for k, v in synth.synth_batch(7, args.batch, args.points, 80, 132).items()}
