@@ -39,6 +39,7 @@ _SIGNATURES = {
     "bd_linear_tc_set_debug": [_P],
     "bd_add_layernorm_f32": [_P, _P, _P, _P, _P, _I, _I, _F, _P],
     "bd_attention_f32": [_P, _I, _LL, _P, _I, _LL, _P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _P],
+    "bd_attention_tc": [_P, _I, _LL, _P, _I, _LL, _P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _I, _P],
     "bd_topk_sigmoid": [_P, _I, _I, _I, _P, _P],
     "bd_l2_normalize_rows": [_P, _P, _I, _I, _P],
     "bd_embedding_rows": [_P, _I, _P, _I, _P, _I, _P],

@@ -275,9 +275,15 @@ class ForwardEngine:
         E, H = self.d_model, self.n_heads
         hd = E // H
         out = self._empty(B * Lq, E)
-        _lib.call("bd_attention_f32", q.data_ptr(), q.stride(0), Lq * q.stride(0), k.data_ptr(), k.stride(0),
-                  Lk * k.stride(0), v.data_ptr(), v.stride(0), Lk * v.stride(0), _lib.ptr(mask), out.data_ptr(), E,
-                  Lq * E, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd))
+        args = (q.data_ptr(), q.stride(0), Lq * q.stride(0), k.data_ptr(), k.stride(0), Lk * k.stride(0),
+                v.data_ptr(), v.stride(0), Lk * v.stride(0), _lib.ptr(mask), out.data_ptr(), E, Lq * E, B, H, Lq, Lk,
+                hd, 1.0 / math.sqrt(hd))
+        aligned = (hd == 36 and q.stride(0) % 4 == 0 and k.stride(0) % 4 == 0 and q.data_ptr() % 16 == 0
+                   and k.data_ptr() % 16 == 0)
+        if self.precision != "fp32" and aligned:
+            _lib.call("bd_attention_tc", *args, self.split)
+        else:
+            _lib.call("bd_attention_f32", *args)
         return out
 
     def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False, res=None, ln_key=None):

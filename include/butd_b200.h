@@ -170,6 +170,15 @@ int bd_attention_f32(const float *Q, int ldq, long long sq_b, const float *K, in
                      const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
                      int B, int H, int Lq, int Lk, int hd, float scale, bd_stream_t stream);
 
+/* Same contract as bd_attention_f32 on the tensor cores (tcgen05.mma, accumulators in TMEM, exact
+ * online softmax in fp32).  head_dim 36 only; Q / K rows 16-byte aligned.  split = 1: bf16
+ * operands; split = 3: bf16 hi/lo split operands for Q·Kᵀ and P·V (fp32-grade). */
+int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk,
+                    long long sk_b, const float *V, int ldv, long long sv_b,
+                    const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
+                    int B, int H, int Lq, int Lk, int hd, float scale, int split,
+                    bd_stream_t stream);
+
 /* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n
  * logits, indices of the k largest sigmoid values, descending, ties -> lower index. n <= 4096 */
 int bd_topk_sigmoid(const float *logits, int B, int n, int k, int *idx, bd_stream_t stream);

@@ -82,3 +82,34 @@ def test_linear_ln_tc(cuda_lib, M, N, K, add, split):
         lin = F.linear(a.double(), W.double(), b.double())
     want = F.layer_norm(R.double() + lin, (N,), gam.double(), bet.double(), 1e-5).float()
     torch.testing.assert_close(Y, want, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 1024, False), (2, 80, 1024, False), (2, 1024, 80, True),
+                                             (3, 256, 132, True), (1, 32, 16, True), (2, 70, 65, True),
+                                             (1, 256, 256, False)])
+def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split):
+    H, hd = 8, 36
+    E = H * hd
+    g = _g(Lq * 7 + Lk)
+    qkv_q = torch.randn(B, Lq, 2 * E, device="cuda", generator=g)  # q lives in a wider fused buffer
+    kv = torch.randn(B, Lk, 2 * E, device="cuda", generator=g)
+    q, k, v = qkv_q[..., :E], kv[..., :E], kv[..., E:]
+    mask = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), generator=torch.Generator().manual_seed(Lk))
+        mask = (torch.arange(Lk)[None] >= lens[:, None]).cuda()
+    out = torch.full((B, Lq, E), float("nan"), device="cuda")
+    m8 = mask.to(torch.uint8).contiguous() if masked else None
+    cuda_lib.call("bd_attention_tc", q.data_ptr(), 2 * E, Lq * 2 * E, k.data_ptr(), 2 * E, Lk * 2 * E,
+                  v.data_ptr(), 2 * E, Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, B, H, Lq, Lk, hd,
+                  1.0 / math.sqrt(hd), split)
+    qh = q.reshape(B, Lq, H, hd).transpose(1, 2).double()
+    kh = k.reshape(B, Lk, H, hd).transpose(1, 2).double()
+    vh = v.reshape(B, Lk, H, hd).transpose(1, 2).double()
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if masked:
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    tol = 2e-2 if split == 1 else 1e-4
+    torch.testing.assert_close(out, want, rtol=tol, atol=tol)
