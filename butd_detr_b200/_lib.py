@@ -39,7 +39,7 @@ _SIGNATURES = {
     "bd_linear_tc_set_debug": [_P],
     "bd_add_layernorm_f32": [_P, _P, _P, _P, _P, _I, _I, _F, _P],
     "bd_attention_f32": [_P, _I, _LL, _P, _I, _LL, _P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _P],
-    "bd_attention_tc": [_P, _I, _LL, _P, _I, _LL, _P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _I, _P],
+    "bd_attention_tc": [_P, _I, _LL, _P, _I, _LL, _P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _I, _P, _P],
     "bd_topk_sigmoid": [_P, _I, _I, _I, _P, _P],
     "bd_l2_normalize_rows": [_P, _P, _I, _I, _P],
     "bd_embedding_rows": [_P, _I, _P, _I, _P, _I, _P],
@@ -48,7 +48,8 @@ _SIGNATURES = {
     "bd_concat_rows": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P],
 }
 
-EXPORTED = sorted(list(_SIGNATURES) + ["bd_version", "bd_last_error", "bd_arch", "bd_fps_resident_capacity"])
+EXPORTED = sorted(list(_SIGNATURES) + ["bd_version", "bd_last_error", "bd_arch", "bd_fps_resident_capacity",
+                                            "bd_attention_tc_workspace_bytes"])
 
 _lib = None
 launch_count = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
@@ -72,6 +73,8 @@ def load():
     lib.bd_last_error.restype = ctypes.c_char_p
     lib.bd_arch.restype = ctypes.c_char_p
     lib.bd_fps_resident_capacity.restype = _I
+    lib.bd_attention_tc_workspace_bytes.restype = _LL
+    lib.bd_attention_tc_workspace_bytes.argtypes = [_I, _I, _I, _I, _I]
     _lib = lib
     return lib
 

@@ -1,24 +1,28 @@
 // Multi-head attention core on tcgen05 — softmax(Q·Kᵀ·scale + mask)·V for nn.MultiheadAttention
 // (call sites /root/reference/models/encoder_decoder_layers.py:87,99,111,149,179,365,373,384,394).
 //
-// One CTA = 128 queries x 1 head x 1 scene; thread t owns query row t (= TMEM lane t).
-// Per tile of 128 keys:
-//   S  = Q·Kᵀ        tcgen05.mma  M=128, N=128, K=64 (head_dim 36 zero-padded to one swizzle block)
-//   softmax           tcgen05.ld of the thread's score row, exact online softmax in fp32
-//                     (running max / sum in registers), probabilities written back to shared
-//                     memory as the bf16 A operand of the second MMA
-//   Ot = P·V          tcgen05.mma  M=128, N=48, K=128 keys into a scratch TMEM accumulator
-//   O  = O·corr + Ot  in registers (36 fp32 per thread), so no TMEM rescaling pass is needed
-// Operands are bf16 hi (+ lo in the "bf16x3" mode: 3 MMAs per product, fp32-grade) in the
-// 128-byte-swizzle K-major layout of tc_common.cuh; Vᵀ is produced by a transposing stage.
-// The softmax scale (and log2 e) is folded into Q, like torch scales q before QKᵀ.
+// Two kernels:
+//  1. attention_pack_kernel — converts the fp32 Q / K / V rows of every (scene, head) ONCE into
+//     bf16 operand tiles (hi, + lo in the "bf16x3" mode) laid out exactly as the tensor core
+//     wants them in shared memory (128-byte swizzle, K-major; Vᵀ via a transposing pass; the
+//     softmax scale·log2e folded into Q; head_dim 36 zero-padded to 64).  A K/V tile is reused by
+//     every 128-query tile of the head, so the conversion is amortised Lq/128 times.
+//  2. attention_tc_kernel — one CTA = 128 queries x 1 head x 1 scene, thread t owns query row t
+//     (= TMEM lane t).  Tiles arrive by cp.async.bulk (TMA engine) on mbarriers, K/V
+//     double-buffered one tile ahead.  Per tile of 128 keys:
+//        S  = Q·Kᵀ        tcgen05.mma  M=128, N=128, K=64
+//        softmax           tcgen05.ld of the thread's score row, exact online softmax in fp32,
+//                          probabilities written to shared memory as the A operand of MMA 2
+//        Ot = P·V          tcgen05.mma  M=128, N=48, K=128 keys into a scratch TMEM accumulator
+//        O  = O·corr + Ot  in registers (36 fp32 per thread): no TMEM rescaling pass
+//     bf16x3: every product is Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32-grade) on the bf16 tensor pipe.
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int AT_BM = 128, AT_BK = 128, AT_NV = 48, AT_THREADS = 128;
-constexpr uint32_t QK_PART = 128 * 128;        // 128 rows x 128 B
-constexpr uint32_t V_BLK = AT_NV * 128;        // 48 rows x 128 B (one block of 64 keys)
+constexpr int AT_BM = 128, AT_BK = 128, AT_NV = 48, AT_THREADS = 128, AT_HD = 36;
+constexpr uint32_t QK_PART = 128 * 128;  // 128 rows x 128 B
+constexpr uint32_t V_BLK = AT_NV * 128;  // 48 rows x 128 B (one block of 64 keys)
 constexpr uint32_t V_PART = 2 * V_BLK;
 constexpr uint32_t P_BLK = 128 * 128;
 constexpr uint32_t P_PART = 2 * P_BLK;
@@ -27,41 +31,112 @@ struct AttnParams {
   const float *Q, *K, *V;
   const unsigned char *mask;
   float *O;
+  unsigned char *Qp, *Kp, *Vp;  // packed operand tiles (workspace)
   int ldq, ldk, ldv, ldo;
   long long sq_b, sk_b, sv_b, so_b;
-  int Lq, Lk, hd;
+  int Lq, Lk, H, nq, nk;
   float scale_log2;
 };
 
+// ------------------------------------------------------------------------------------------ pack
+// grid.x = nq + 2 * nk : [0,nq) Q tiles, [nq,nq+nk) K tiles, rest V tiles ; grid.y = H ; grid.z = B
+template <int PARTS>
+__global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p) {
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, h = blockIdx.y;
+  int t = blockIdx.x;
+  if (t < p.nq + p.nk) {
+    // ---- row tiles (Q or K): item = (row, 16-byte chunk of 8 head dims); chunks 5..7 are padding
+    const bool is_q = t < p.nq;
+    if (!is_q) t -= p.nq;
+    const float *src = is_q ? p.Q + b * p.sq_b : p.K + b * p.sk_b;
+    const int ld = is_q ? p.ldq : p.ldk, n_rows = is_q ? p.Lq : p.Lk, row0 = t * 128;
+    const float mul = is_q ? p.scale_log2 : 1.0f;
+    unsigned char *dst = (is_q ? p.Qp + (static_cast<size_t>(b) * p.H + h) * p.nq * (PARTS * QK_PART)
+                               : p.Kp + (static_cast<size_t>(b) * p.H + h) * p.nk * (PARTS * QK_PART)) +
+                         static_cast<size_t>(t) * (PARTS * QK_PART);
+    src += h * AT_HD;
+    // 128 rows x 8 chunks = 1024 items, 4 per thread, loads batched
+    float4 a[4][2];
+    int rr[4], cc[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = tid + it * 256;
+      const int r = e & 127, ch = e >> 7;  // consecutive threads -> consecutive rows
+      rr[it] = r, cc[it] = ch;
+      a[it][0] = a[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < n_rows && ch * 8 < AT_HD) {
+        const float4 *s = reinterpret_cast<const float4 *>(src + static_cast<long long>(row0 + r) * ld + ch * 8);
+        a[it][0] = __ldg(s);
+        if (ch * 8 + 4 < AT_HD) a[it][1] = __ldg(s + 1);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const float v[8] = {a[it][0].x * mul, a[it][0].y * mul, a[it][0].z * mul, a[it][0].w * mul,
+                          a[it][1].x * mul, a[it][1].y * mul, a[it][1].z * mul, a[it][1].w * mul};
+      uint4 hi, lo;
+      tc::split_bf16x8(v, hi, lo);
+      const uint32_t off = tc::sw128_off(rr[it], cc[it]);
+      *reinterpret_cast<uint4 *>(dst + off) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + QK_PART + off) = lo;
+    }
+  } else {
+    // ---- V^T tile: rows = head dims (48, 36 valid), K = 128 keys in two blocks of 64
+    t -= p.nq + p.nk;
+    const float *src = p.V + b * p.sv_b + h * AT_HD;
+    const int k0 = t * 128;
+    unsigned char *dst = p.Vp + ((static_cast<size_t>(b) * p.H + h) * p.nk + t) * (PARTS * V_PART);
+    // 48 rows x 16 key-chunks = 768 items, 3 per thread; item = 8 keys of one head dim
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      const int e = tid + it * 256;
+      const int d = e % AT_NV, kc = e / AT_NV;  // consecutive threads -> consecutive head dims (coalesced)
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = k0 + kc * 8 + i;
+        v[i] = (d < AT_HD && key < p.Lk) ? __ldg(src + static_cast<long long>(key) * p.ldv + d) : 0.f;
+      }
+      uint4 hi, lo;
+      tc::split_bf16x8(v, hi, lo);
+      const uint32_t off = (kc >> 3) * V_BLK + tc::sw128_off(d, kc & 7);
+      *reinterpret_cast<uint4 *>(dst + off) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + V_PART + off) = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ main
 template <int PARTS>
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char *sQ = smem;
-  unsigned char *sK = sQ + PARTS * QK_PART;
-  unsigned char *sV = sK + PARTS * QK_PART;
-  unsigned char *sP = sV + PARTS * V_PART;  // 1024-aligned: V_PART = 12 KB
-  __shared__ __align__(8) unsigned long long bar;
+  constexpr uint32_t KV_STAGE = PARTS * (QK_PART + V_PART);
+  unsigned char *sQ = smem;                     // PARTS * 16 KB
+  unsigned char *sKV = sQ + PARTS * QK_PART;    // 2 stages x (K: PARTS*16 KB, V: PARTS*12 KB)
+  unsigned char *sP = sKV + 2 * KV_STAGE;       // PARTS * 32 KB
+  __shared__ __align__(8) unsigned long long bar_mma, bar_q, bar_kv[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ unsigned char kvalid[AT_BK];
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BM;
-  constexpr int hd = 36;  // enforced by the host wrapper (d_model 288 / 8 heads)
-  const float *Qg = p.Q + b * p.sq_b + h * hd;
-  const float *Kg = p.K + b * p.sk_b + h * hd;
-  const float *Vg = p.V + b * p.sv_b + h * hd;
+  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x, q0 = qt * AT_BM;
   const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
+  const size_t bh = static_cast<size_t>(b) * p.H + h;
+  const unsigned char *Qp = p.Qp + (bh * p.nq + qt) * (PARTS * QK_PART);
+  const unsigned char *Kp = p.Kp + bh * p.nk * (PARTS * QK_PART);
+  const unsigned char *Vp = p.Vp + bh * p.nk * (PARTS * V_PART);
 
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 256);
   if (tid == 32) {
-    tc::mbar_init(tc::smem_u32(&bar), 1);
+    tc::mbar_init(tc::smem_u32(&bar_mma), 1);
+    tc::mbar_init(tc::smem_u32(&bar_q), 1);
+    tc::mbar_init(tc::smem_u32(&bar_kv[0]), 1);
+    tc::mbar_init(tc::smem_u32(&bar_kv[1]), 1);
     tc::fence_mbar_init();
   }
-  // zero the operand tiles once: padded head dims / padded V rows stay zero for the whole kernel
-  for (uint32_t i = tid; i < (PARTS * (2 * QK_PART + V_PART)) / 16; i += AT_THREADS)
-    reinterpret_cast<uint4 *>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -69,68 +144,45 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
   const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
 
-  // rows of Q / K: (row, 16-byte chunk) items, chunk = 8 head dims; hd = 36 -> chunks 0..4
-  const int n_ch = (hd + 7) / 8;
-  auto stage_rows = [&](unsigned char *dst, const float *src, int ld, int row0, int n_rows, float mul) {
-    for (int e = tid; e < AT_BM * n_ch; e += AT_THREADS) {
-      const int r = e % AT_BM, ch = e / AT_BM;  // consecutive threads -> consecutive rows (conflict-free stores)
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (row0 + r < n_rows) {
-        const float *s = src + static_cast<long long>(row0 + r) * ld + ch * 8;
-        const int nv = min(8, hd - ch * 8);
-        if (nv == 8) {
-          const float4 a = __ldg(reinterpret_cast<const float4 *>(s)), c = __ldg(reinterpret_cast<const float4 *>(s) + 1);
-          v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = c.x, v[5] = c.y, v[6] = c.z, v[7] = c.w;
-        } else {
-          for (int i = 0; i < nv; ++i) v[i] = __ldg(s + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= mul;
-      }
-      uint4 hi, lo;
-      tc::split_bf16x8(v, hi, lo);
-      const uint32_t off = tc::sw128_off(r, ch);
-      *reinterpret_cast<uint4 *>(dst + off) = hi;
-      if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + QK_PART + off) = lo;
-    }
+  auto issue_kv = [&](int j) {  // thread 0: K and V^T tiles of key tile j -> stage j & 1
+    const uint32_t st = j & 1;
+    const uint32_t bar = tc::smem_u32(&bar_kv[st]);
+    tc::mbar_arrive_expect_tx(bar, KV_STAGE);
+    tc::bulk_g2s(tc::smem_u32(sKV + st * KV_STAGE), Kp + static_cast<size_t>(j) * (PARTS * QK_PART), PARTS * QK_PART, bar);
+    tc::bulk_g2s(tc::smem_u32(sKV + st * KV_STAGE + PARTS * QK_PART), Vp + static_cast<size_t>(j) * (PARTS * V_PART),
+                 PARTS * V_PART, bar);
   };
-  stage_rows(sQ, Qg, p.ldq, q0, p.Lq, p.scale_log2);
+  if (tid == 0) {
+    tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_q), PARTS * QK_PART);
+    tc::bulk_g2s(tc::smem_u32(sQ), Qp, PARTS * QK_PART, tc::smem_u32(&bar_q));
+    issue_kv(0);
+  }
 
   float m_run = -INFINITY, l_run = 0.f;
-  float o_acc[36];
+  float o_acc[AT_HD];
 #pragma unroll
-  for (int i = 0; i < 36; ++i) o_acc[i] = 0.f;
+  for (int i = 0; i < AT_HD; ++i) o_acc[i] = 0.f;
   uint32_t phase = 0;
   const uint32_t idesc_s = tc::idesc_bf16(AT_BM, AT_BK), idesc_o = tc::idesc_bf16(AT_BM, AT_NV);
+  const int n_tiles = p.nk;
 
-  for (int k0 = 0; k0 < p.Lk; k0 += AT_BK) {
-    // ---- stage K tile (rows = keys) and V^T tile (rows = head dims, K = keys)
-    stage_rows(sK, Kg, p.ldk, k0, p.Lk, 1.0f);
-    for (int e = tid; e < hd * (AT_BK / 8); e += AT_THREADS) {
-      const int d = e % hd, kc = e / hd;  // consecutive threads -> consecutive head dims (coalesced)
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int key = k0 + kc * 8 + i;
-        v[i] = key < p.Lk ? __ldg(Vg + static_cast<long long>(key) * p.ldv + d) : 0.f;
-      }
-      uint4 hi, lo;
-      tc::split_bf16x8(v, hi, lo);
-      const uint32_t off = (kc >> 3) * V_BLK + tc::sw128_off(d, kc & 7);
-      *reinterpret_cast<uint4 *>(sV + off) = hi;
-      if (PARTS == 2) *reinterpret_cast<uint4 *>(sV + V_PART + off) = lo;
-    }
-    kvalid[tid] = (k0 + tid < p.Lk) && !(mask && mask[k0 + tid]);
-    tc::fence_proxy_async_smem();
-    __syncthreads();
+  for (int j = 0; j < n_tiles; ++j) {
+    const uint32_t st = j & 1;
+    const int k0 = j * AT_BK;
+    // prefetch the next K/V tile into the other stage (its previous MMAs were waited for by
+    // every thread at the end of the last iteration)
+    if (tid == 0 && j + 1 < n_tiles) issue_kv(j + 1);
+    const bool my_valid = (k0 + tid < p.Lk) && !(mask && mask[k0 + tid]);
+    kvalid[tid] = my_valid;
+    const bool all_valid = __syncthreads_and(my_valid);  // common case: full, unmasked tile
 
     // ---- S = Q K^T
     if (warp == 0) {
+      if (j == 0) tc::mbar_wait(tc::smem_u32(&bar_q), 0);
+      tc::mbar_wait(tc::smem_u32(&bar_kv[st]), (j >> 1) & 1);
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t q = tc::smem_u32(sQ), k = tc::smem_u32(sK);
+        const uint32_t q = tc::smem_u32(sQ), k = tc::smem_u32(sKV + st * KV_STAGE);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           const uint64_t dq = tc::smem_desc_sw128(q + s * 32), dk = tc::smem_desc_sw128(k + s * 32);
@@ -140,39 +192,54 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
             tc::mma_bf16(tmem_s, dq, tc::smem_desc_sw128(k + QK_PART + s * 32), idesc_s, 1u);
           }
         }
-        tc::mma_commit(tc::smem_u32(&bar));
+        tc::mma_commit(tc::smem_u32(&bar_mma));
       }
       __syncwarp();
     }
-    tc::mbar_wait(tc::smem_u32(&bar), phase);
+    tc::mbar_wait(tc::smem_u32(&bar_mma), phase);
     phase ^= 1u;
     tc::fence_after_sync();
 
     // ---- online softmax on the thread's row (two passes over TMEM: max, then exp / sum / pack)
     float mx = -INFINITY;
 #pragma unroll
-    for (int g = 0; g < AT_BK / 16; ++g) {
-      uint32_t acc[16];
-      tc::tmem_ld16(tmem_s + lane_base + g * 16, acc);
+    for (int g = 0; g < AT_BK / 16; g += 2) {
+      uint32_t acc0[16], acc1[16];
+      tc::tmem_ld16(tmem_s + lane_base + g * 16, acc0);
+      tc::tmem_ld16(tmem_s + lane_base + (g + 1) * 16, acc1);
       tc::tmem_ld_wait();
+      if (all_valid) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (kvalid[g * 16 + j]) mx = fmaxf(mx, __uint_as_float(acc[j]));
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(acc0[i]), __uint_as_float(acc1[i])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (kvalid[g * 16 + i]) mx = fmaxf(mx, __uint_as_float(acc0[i]));
+          if (kvalid[(g + 1) * 16 + i]) mx = fmaxf(mx, __uint_as_float(acc1[i]));
+        }
+      }
     }
     const float m_new = fmaxf(m_run, mx);
     const float corr = (m_new == -INFINITY) ? 1.f : exp2f(m_run - m_new);
     float sum = 0.f;
-    const int r = tid;
 #pragma unroll
     for (int g = 0; g < AT_BK / 16; ++g) {
       uint32_t acc[16];
       tc::tmem_ld16(tmem_s + lane_base + g * 16, acc);
       tc::tmem_ld_wait();
       float pv[16];
+      if (all_valid) {  // m_new is finite here
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        pv[j] = (kvalid[g * 16 + j] && m_new != -INFINITY) ? exp2f(__uint_as_float(acc[j]) - m_new) : 0.f;
-        sum += pv[j];
+        for (int i = 0; i < 16; ++i) {
+          pv[i] = exp2f(__uint_as_float(acc[i]) - m_new);
+          sum += pv[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pv[i] = (kvalid[g * 16 + i] && m_new != -INFINITY) ? exp2f(__uint_as_float(acc[i]) - m_new) : 0.f;
+          sum += pv[i];
+        }
       }
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
@@ -181,7 +248,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
         uint4 hi, lo;
         tc::split_bf16x8(v8, hi, lo);
         const int kc = g * 2 + c2;  // 16-byte chunk of keys
-        const uint32_t off = (kc >> 3) * P_BLK + tc::sw128_off(r, kc & 7);
+        const uint32_t off = (kc >> 3) * P_BLK + tc::sw128_off(tid, kc & 7);
         *reinterpret_cast<uint4 *>(sP + off) = hi;
         if (PARTS == 2) *reinterpret_cast<uint4 *>(sP + P_PART + off) = lo;
       }
@@ -196,7 +263,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
     if (warp == 0) {
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t pa = tc::smem_u32(sP), va = tc::smem_u32(sV);
+        const uint32_t pa = tc::smem_u32(sP), va = tc::smem_u32(sKV + st * KV_STAGE + PARTS * QK_PART);
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
@@ -210,11 +277,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
             }
           }
         }
-        tc::mma_commit(tc::smem_u32(&bar));
+        tc::mma_commit(tc::smem_u32(&bar_mma));
       }
       __syncwarp();
     }
-    tc::mbar_wait(tc::smem_u32(&bar), phase);
+    tc::mbar_wait(tc::smem_u32(&bar_mma), phase);
     phase ^= 1u;
     tc::fence_after_sync();
     {
@@ -224,22 +291,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
       tc::tmem_ld16(tmem_o + lane_base + 32, a2);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o_acc[j] = fmaf(o_acc[j], corr, __uint_as_float(a0[j]));
+      for (int i = 0; i < 16; ++i) o_acc[i] = fmaf(o_acc[i], corr, __uint_as_float(a0[i]));
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o_acc[16 + j] = fmaf(o_acc[16 + j], corr, __uint_as_float(a1[j]));
+      for (int i = 0; i < 16; ++i) o_acc[16 + i] = fmaf(o_acc[16 + i], corr, __uint_as_float(a1[i]));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o_acc[32 + j] = fmaf(o_acc[32 + j], corr, __uint_as_float(a2[j]));
+      for (int i = 0; i < 4; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], corr, __uint_as_float(a2[i]));
     }
     tc::fence_before_sync();
-    __syncthreads();  // K / V / P tiles and both accumulators are free for the next key tile
+    __syncthreads();  // stage st, the P tile, kvalid and both accumulators are free again
   }
 
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
   if (q0 + tid < p.Lq) {
-    float *dst = p.O + b * p.so_b + static_cast<long long>(q0 + tid) * p.ldo + h * hd;
+    float *dst = p.O + b * p.so_b + static_cast<long long>(q0 + tid) * p.ldo + h * AT_HD;
     const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
 #pragma unroll
-    for (int d = 0; d < hd; d += 4) {
+    for (int d = 0; d < AT_HD; d += 4) {
       float4 o4 = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
       if (l_run == 0.f) o4 = make_float4(NAN, NAN, NAN, NAN);
       dst[d] = o4.x, dst[d + 1] = o4.y, dst[d + 2] = o4.z, dst[d + 3] = o4.w;
@@ -249,38 +316,54 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
 
 }  // namespace
 
+extern "C" long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int split) {
+  const long long parts = split == 3 ? 2 : 1;
+  const long long nq = (Lq + 127) / 128, nk = (Lk + 127) / 128;
+  return static_cast<long long>(B) * H * parts * (nq * QK_PART + nk * (QK_PART + V_PART));
+}
+
 extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
                                const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
                                float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
-                               int split, bd_stream_t stream) {
-  BD_REQUIRE(Q && K && V && O, "bd_attention_tc: null pointer");
+                               int split, void *workspace, bd_stream_t stream) {
+  BD_REQUIRE(Q && K && V && O && workspace, "bd_attention_tc: null pointer");
   BD_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && B <= 65535 && H <= 65535, "bd_attention_tc: bad sizes");
-  BD_REQUIRE(hd == 36, "bd_attention_tc: built for head_dim 36 (d_model 288 / 8 heads)");
+  BD_REQUIRE(hd == AT_HD, "bd_attention_tc: built for head_dim 36 (d_model 288 / 8 heads)");
   BD_REQUIRE(split == 1 || split == 3, "bd_attention_tc: split must be 1 (bf16) or 3 (bf16x3)");
   BD_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && sq_b % 4 == 0 && sk_b % 4 == 0 &&
-                 (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0,
-             "bd_attention_tc: Q / K rows must be 16-byte aligned");
+                 (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+             "bd_attention_tc: Q / K rows and the workspace must be 16-byte aligned");
   AttnParams p = {};
   p.Q = Q, p.K = K, p.V = V, p.mask = key_padding_mask, p.O = O;
   p.ldq = ldq, p.ldk = ldk, p.ldv = ldv, p.ldo = ldo;
   p.sq_b = sq_b, p.sk_b = sk_b, p.sv_b = sv_b, p.so_b = so_b;
-  p.Lq = Lq, p.Lk = Lk, p.hd = hd;
+  p.Lq = Lq, p.Lk = Lk, p.H = H;
+  p.nq = bd::ceil_div(Lq, AT_BM), p.nk = bd::ceil_div(Lk, AT_BK);
   p.scale_log2 = scale * 1.4426950408889634f;
-  const int parts = split == 3 ? 2 : 1;
-  const size_t smem = static_cast<size_t>(parts) * (2 * QK_PART + V_PART + P_PART) + 1024;
+  const size_t parts = split == 3 ? 2 : 1;
+  unsigned char *ws = static_cast<unsigned char *>(workspace);
+  p.Qp = ws;
+  p.Kp = p.Qp + static_cast<size_t>(B) * H * p.nq * parts * QK_PART;
+  p.Vp = p.Kp + static_cast<size_t>(B) * H * p.nk * parts * QK_PART;
+  const size_t smem = parts * (QK_PART + 2 * (QK_PART + V_PART) + P_PART) + 1024;
   static thread_local bool configured = false;
   if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
             "bd_attention_tc");
-    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
             "bd_attention_tc");
     configured = true;
   }
-  dim3 grid(bd::ceil_div(Lq, AT_BM), H, B);
-  if (parts == 2)
-    attention_tc_kernel<2><<<grid, AT_THREADS, smem, bd::as_stream(stream)>>>(p);
-  else
-    attention_tc_kernel<1><<<grid, AT_THREADS, smem, bd::as_stream(stream)>>>(p);
+  cudaStream_t s = bd::as_stream(stream);
+  dim3 pgrid(p.nq + 2 * p.nk, H, B), grid(p.nq, H, B);
+  if (parts == 2) {
+    attention_pack_kernel<2><<<pgrid, 256, 0, s>>>(p);
+    attention_tc_kernel<2><<<grid, AT_THREADS, smem, s>>>(p);
+  } else {
+    attention_pack_kernel<1><<<pgrid, 256, 0, s>>>(p);
+    attention_tc_kernel<1><<<grid, AT_THREADS, smem, s>>>(p);
+  }
   BD_CHECK_LAUNCH("bd_attention_tc");
   return BD_OK;
 }

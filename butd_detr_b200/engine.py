@@ -281,7 +281,8 @@ class ForwardEngine:
         aligned = (hd == 36 and q.stride(0) % 4 == 0 and k.stride(0) % 4 == 0 and q.data_ptr() % 16 == 0
                    and k.data_ptr() % 16 == 0)
         if self.precision != "fp32" and aligned:
-            _lib.call("bd_attention_tc", *args, self.split)
+            ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
+            _lib.call("bd_attention_tc", *args, self.split, ws.data_ptr())
         else:
             _lib.call("bd_attention_f32", *args)
         return out

@@ -172,11 +172,14 @@ int bd_attention_f32(const float *Q, int ldq, long long sq_b, const float *K, in
 
 /* Same contract as bd_attention_f32 on the tensor cores (tcgen05.mma, accumulators in TMEM, exact
  * online softmax in fp32).  head_dim 36 only; Q / K rows 16-byte aligned.  split = 1: bf16
- * operands; split = 3: bf16 hi/lo split operands for Q·Kᵀ and P·V (fp32-grade). */
+ * operands; split = 3: bf16 hi/lo split operands for Q·Kᵀ and P·V (fp32-grade).  `workspace`:
+ * bd_attention_tc_workspace_bytes(...) bytes of device scratch (16-byte aligned) that receives the
+ * packed bf16 operand tiles (a pack kernel runs first, then the tensor-core kernel). */
+long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int split);
 int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk,
                     long long sk_b, const float *V, int ldv, long long sv_b,
                     const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
-                    int B, int H, int Lq, int Lk, int hd, float scale, int split,
+                    int B, int H, int Lq, int Lk, int hd, float scale, int split, void *workspace,
                     bd_stream_t stream);
 
 /* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n

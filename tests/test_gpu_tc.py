@@ -101,9 +101,10 @@ def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split):
         mask = (torch.arange(Lk)[None] >= lens[:, None]).cuda()
     out = torch.full((B, Lq, E), float("nan"), device="cuda")
     m8 = mask.to(torch.uint8).contiguous() if masked else None
+    ws = torch.empty(cuda_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, split), dtype=torch.uint8, device="cuda")
     cuda_lib.call("bd_attention_tc", q.data_ptr(), 2 * E, Lq * 2 * E, k.data_ptr(), 2 * E, Lk * 2 * E,
                   v.data_ptr(), 2 * E, Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, B, H, Lq, Lk, hd,
-                  1.0 / math.sqrt(hd), split)
+                  1.0 / math.sqrt(hd), split, ws.data_ptr())
     qh = q.reshape(B, Lq, H, hd).transpose(1, 2).double()
     kh = k.reshape(B, Lk, H, hd).transpose(1, 2).double()
     vh = v.reshape(B, Lk, H, hd).transpose(1, 2).double()
