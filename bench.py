@@ -282,7 +282,7 @@ def main():
                 "e2e": {"value": scenes / (e2e_ms * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "kernels": kernel_table[:8] if kernel_table else None}
+                "cpu_baseline": cpu_baseline, "kernels": kernel_table[:40] if kernel_table else None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "bd_gather_points": [_P, _P, _I, _I, _I, _I, _P, _P],
     "bd_gather_points_grad": [_P, _P, _I, _I, _I, _I, _P, _P],
     "bd_ball_query": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P],
+    "bd_ball_query_grid": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P],
     "bd_group_points": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "bd_group_points_grad": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "bd_three_nn": [_P, _P, _I, _I, _I, _P, _P, _P],
@@ -49,7 +50,7 @@ _SIGNATURES = {
 }
 
 EXPORTED = sorted(list(_SIGNATURES) + ["bd_version", "bd_last_error", "bd_arch", "bd_fps_resident_capacity",
-                                            "bd_attention_tc_workspace_bytes"])
+                                            "bd_attention_tc_workspace_bytes", "bd_ball_query_grid_workspace_bytes"])
 
 _lib = None
 launch_count = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
@@ -73,6 +74,8 @@ def load():
     lib.bd_last_error.restype = ctypes.c_char_p
     lib.bd_arch.restype = ctypes.c_char_p
     lib.bd_fps_resident_capacity.restype = _I
+    lib.bd_ball_query_grid_workspace_bytes.restype = _LL
+    lib.bd_ball_query_grid_workspace_bytes.argtypes = [_I, _I]
     lib.bd_attention_tc_workspace_bytes.restype = _LL
     lib.bd_attention_tc_workspace_bytes.argtypes = [_I, _I, _I, _I, _I]
     _lib = lib

@@ -316,7 +316,22 @@ extern "C" int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp,
   else {
     // latency mode (few scenes): 16-CTA clusters halve the per-round register sweep;
     // throughput mode: 8-CTA clusters keep up to 18 scenes in flight on 148 SMs.
-    int cluster = g_force_cluster > 0 ? g_force_cluster : (B <= 8 ? 16 : 8);
+    // measured on B200 (50k points): 16-CTA clusters win up to 4 scenes (1.34 vs 1.56 ms); from 8
+    // scenes on only ~6 of them are co-resident (one per GPC) and 8-CTA clusters win (1.56 vs 1.92 ms);
+    // beyond 8 scenes 4-CTA clusters (25 points per thread) keep up to 37 scenes in a single wave
+    // (2.18 ms for 16-32 scenes vs 3.1-4.6 ms with 8-CTA clusters).
+    int cluster = g_force_cluster > 0 ? g_force_cluster : (B <= 4 ? 16 : (B <= 8 ? 8 : 4));
+    if (cluster == 4 && R > 4 * T * 25) cluster = 8;
+    if (cluster == 4) {
+      e = launch_resident<4, 25>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        bd::set_error("bd_fps: launch failed: %s", cudaGetErrorString(e));
+        return BD_ERR_CUDA;
+      }
+      BD_CHECK_LAUNCH("bd_fps");
+      return BD_OK;
+    }
     if (cluster == 16 && R <= 16 * T * 16) {
       if (R <= 16 * T * 4) e = launch_resident<16, 4>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
       else if (R <= 16 * T * 7) e = launch_resident<16, 7>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);

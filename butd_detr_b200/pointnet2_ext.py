@@ -14,6 +14,9 @@ import torch
 from . import _lib
 
 
+GRID_MIN_POINTS = 8192  # clouds at least this large use the cell-list ball query
+
+
 def _check(t, name, dtype):
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be a contiguous tensor")
@@ -67,8 +70,15 @@ def ball_query(new_xyz, xyz, radius, nsample):
     n = xyz.shape[1]
     out = torch.zeros(B, m, nsample, dtype=torch.int32, device=xyz.device)
     with torch.cuda.device(xyz.device):
-        _lib.call("bd_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), 3, B, n, m, float(radius), int(nsample),
-                  out.data_ptr())
+        # cell-list search (identical output): pays off when the ball holds about nsample points;
+        # for small nsample the ordered brute-force scan exits early and wins (measured)
+        if n >= GRID_MIN_POINTS and nsample >= 48:
+            ws = torch.empty(_lib.load().bd_ball_query_grid_workspace_bytes(B, n), dtype=torch.uint8, device=xyz.device)
+            _lib.call("bd_ball_query_grid", new_xyz.data_ptr(), xyz.data_ptr(), 3, B, n, m, float(radius),
+                      int(nsample), out.data_ptr(), ws.data_ptr())
+        else:
+            _lib.call("bd_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), 3, B, n, m, float(radius), int(nsample),
+                      out.data_ptr())
     return out
 
 

@@ -73,6 +73,15 @@ int bd_gather_points_grad(const float *grad_out, const int *idx, int B, int C, i
 int bd_ball_query(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
                   float radius, int nsample, int *idx, bd_stream_t stream);
 
+/* Same result as bd_ball_query, bit for bit, through a per-scene uniform grid (cell list): points
+ * are binned into cells of edge >= radius, each centre visits its 27 neighbour cells and the
+ * `nsample` smallest in-ball indices are selected by rank, restoring the reference's index order.
+ * Replaces the 102 M brute-force distance tests per scene of ball_query_gpu.cu:14-49 at SA1 by
+ * ~0.5 M.  `workspace`: bd_ball_query_grid_workspace_bytes(B, n) bytes of device scratch. */
+long long bd_ball_query_grid_workspace_bytes(int B, int n);
+int bd_ball_query_grid(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
+                       float radius, int nsample, int *idx, void *workspace, bd_stream_t stream);
+
 /* group_points(points (B,C,n), idx (B,m,ns)) -> out (B,C,m,ns)   group_points.cpp:17-40 */
 int bd_group_points(const float *points, const int *idx, int B, int C, int n, int m, int ns,
                     float *out, bd_stream_t stream);

@@ -160,3 +160,37 @@ def test_reference_python_runs_unmodified_on_the_drop_in(ext, oracle_lib):
     from oracle import model_ref
     want = model_ref.query_and_group(xyz, new_xyz, feats, 0.3, 16)
     torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+
+
+GRID_CASES = BALL_CASES + [("dense_overflow", "dup", 1, 6000, 64, 2.0, 32), ("wide", "uniform", 2, 9000, 300, 1.7, 16)]
+
+
+@pytest.mark.parametrize("case", GRID_CASES, ids=[c[0] for c in GRID_CASES])
+def test_ball_query_grid_equals_bruteforce(case, cuda_lib, oracle_lib):
+    """Cell-list ball query == ordered brute force, bit for bit (incl. > 768-hit balls, empty balls,
+    centres outside the cloud's bounding box, d2 == r2 lattice ties)."""
+    xyz, new_xyz, r, ns = ball_inputs(case) if case in BALL_CASES else (
+        cloud(case_seed(case[0]), case[3], case[1], case[2]), cloud(77, case[4], "uniform", case[2]) * 1.2, case[5], case[6])
+    B, n, m = xyz.shape[0], xyz.shape[1], new_xyz.shape[1]
+    want = oracle_lib.ball_query(new_xyz.contiguous(), xyz, r, ns)
+    xd, cd = xyz.cuda(), new_xyz.contiguous().cuda()
+    out = torch.full((B, m, ns), -1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(cuda_lib.load().bd_ball_query_grid_workspace_bytes(B, n), dtype=torch.uint8, device="cuda")
+    cuda_lib.call("bd_ball_query_grid", cd.data_ptr(), xd.data_ptr(), 3, B, n, m, float(r), ns, out.data_ptr(),
+                  ws.data_ptr())
+    assert torch.equal(out.cpu(), want)
+
+
+def test_ball_query_grid_full_scene_sweep(cuda_lib, oracle_lib):
+    """BASELINE.json configs[4]: 50k points, nsample in {16,32,64} x radius in {0.2,0.4,0.8}."""
+    xyz = cloud(21, 50000, "room", 1)
+    inds = oracle_lib.furthest_point_sampling(xyz, 2048)
+    new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    xd, cd = xyz.cuda(), new_xyz.cuda()
+    ws = torch.empty(cuda_lib.load().bd_ball_query_grid_workspace_bytes(1, 50000), dtype=torch.uint8, device="cuda")
+    for r in (0.2, 0.4, 0.8):
+        for ns in (16, 32, 64):
+            out = torch.full((1, 2048, ns), -1, dtype=torch.int32, device="cuda")
+            cuda_lib.call("bd_ball_query_grid", cd.data_ptr(), xd.data_ptr(), 3, 1, 50000, 2048, r, ns, out.data_ptr(),
+                          ws.data_ptr())
+            assert torch.equal(out.cpu(), oracle_lib.ball_query(new_xyz, xyz, r, ns)), (r, ns)
