@@ -37,6 +37,13 @@ struct LinearTcParams {
   int lda, lda2, ldy, ldr;
   int M, N, K, n_chunks, BN, n_sub, relu, split, n_stages;
   float eps;
+  // gather mode (QueryAndGroup fused into the A staging): row r = (scene b, centre j, sample s),
+  // A[r, :] = [ feats[b, idx[r], 0:C] | (xyz[b, idx[r]] - centre[b, j]) * inv_radius | 0 ... ]
+  const int *g_idx;
+  const float *g_feat, *g_xyz, *g_cen;
+  int g_ldf, g_ldx, g_C, g_ns, g_n, g_m;
+  float g_inv_r;
+  int pool;  // > 0: max over groups of `pool` consecutive rows in the epilogue (F.max_pool2d over nsample)
   long long *dbg;  // optional clock64() stamps of CTA (0,0), thread 0 (tuning aid)
 };
 
@@ -45,8 +52,13 @@ struct LinearTcParams {
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[i] = clock64();    \
   } while (0)
 
-template <bool LN_EPI, bool HAS_A2>
-__global__ void __launch_bounds__(TC_THREADS, HAS_A2 ? 1 : 2) linear_tc_kernel(const LinearTcParams p) {
+// MODE: 0 = A, 1 = A + A2, 2 = gathered rows (QueryAndGroup).  EPI: 0 = bias/ReLU, 1 = residual + LayerNorm,
+// 2 = bias/ReLU + max-pool over groups of rows.
+template <int EPI, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, MODE == 0 ? 2 : 1) linear_tc_kernel(const LinearTcParams p) {
+  constexpr bool LN_EPI = EPI == 1;
+  constexpr bool HAS_A2 = MODE == 1;
+  constexpr bool GATHER = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // swizzle-128B tiles need 1024-byte aligned bases (in the shared address space)
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -84,7 +96,7 @@ __global__ void __launch_bounds__(TC_THREADS, HAS_A2 ? 1 : 2) linear_tc_kernel(c
   // Per-thread staging plan, identical for every k-chunk.  A warp-item covers 8 rows x 4 chunks
   // (lane = chunk_local * 8 + row_local): 128 contiguous bytes per row from global memory and
   // conflict-free 16-byte st.shared into the swizzled tile.
-  long long g_off[TC_ITEMS], g2_off[TC_ITEMS];
+  long long g_off[TC_ITEMS], g2_off[TC_ITEMS], s_cen[TC_ITEMS];
   uint32_t s_off[TC_ITEMS];
   int k_off[TC_ITEMS];
   bool row_ok[TC_ITEMS];
@@ -97,12 +109,43 @@ __global__ void __launch_bounds__(TC_THREADS, HAS_A2 ? 1 : 2) linear_tc_kernel(c
     s_off[it] = tc::sw128_off(r, ch);
     g_off[it] = static_cast<long long>(row0 + r) * p.lda + ch * 8;
     g2_off[it] = static_cast<long long>(row0 + r) * p.lda2 + ch * 8;
+    if (GATHER) {  // g_off -> gathered feature row, g2_off -> gathered xyz row; centre kept in cen[]
+      const long long gr = row_ok[it] ? row0 + r : 0;
+      const int a = __ldg(p.g_idx + gr);
+      const long long bj = gr / p.g_ns, b = bj / p.g_m;
+      g_off[it] = (b * p.g_n + a) * p.g_ldf;
+      g2_off[it] = (b * p.g_n + a) * p.g_ldx;
+      s_cen[it] = bj * 3;
+    }
   }
   float4 ra0[TC_ITEMS][2], rb0[TC_ITEMS][2], ra1[TC_ITEMS][2], rb1[TC_ITEMS][2];
   auto issue_loads = [&](int c, float4 (&ra)[TC_ITEMS][2], float4 (&rb)[TC_ITEMS][2]) {
 #pragma unroll
     for (int it = 0; it < TC_ITEMS; ++it) {
       const bool ok = row_ok[it] && (c * KC + k_off[it] < p.K);  // K % 8 == 0: whole item in range
+      if (GATHER) {
+        const int k0 = c * KC + k_off[it];
+        const float *f = p.g_feat + g_off[it];
+        if (ok && k0 + 8 <= p.g_C && ((p.g_ldf | p.g_C) & 3) == 0) {  // chunk entirely inside the feature row
+          ra[it][0] = __ldg(reinterpret_cast<const float4 *>(f + k0));
+          ra[it][1] = __ldg(reinterpret_cast<const float4 *>(f + k0) + 1);
+        } else {  // chunk straddles features / relative xyz / padding
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            float x = 0.f;
+            if (ok && k < p.g_C) x = __ldg(f + k);
+            else if (ok && k < p.g_C + 3)
+              x = __fmul_rn(__fsub_rn(__ldg(p.g_xyz + g2_off[it] + (k - p.g_C)), __ldg(p.g_cen + s_cen[it] + (k - p.g_C))),
+                            p.g_inv_r);
+            v[i] = x;
+          }
+          ra[it][0] = make_float4(v[0], v[1], v[2], v[3]);
+          ra[it][1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        continue;
+      }
       const float4 *src = reinterpret_cast<const float4 *>(p.A + (ok ? g_off[it] + c * KC : 0));
       ra[it][0] = __ldg(src), ra[it][1] = __ldg(src + 1);
       if (HAS_A2) {
@@ -247,7 +290,19 @@ __global__ void __launch_bounds__(TC_THREADS, HAS_A2 ? 1 : 2) linear_tc_kernel(c
 
   // ---- epilogue 2: warp-per-row coalesced write-out
   const int n_valid = min(NC, p.N - col_base);
-  if (!LN_EPI) {
+  if (EPI == 2) {
+    // max over groups of `pool` consecutive rows (the nsample neighbours of one centre); M % pool == 0
+    const int groups = TC_BM / p.pool;
+    for (int e = tid; e < groups * n_valid; e += TC_THREADS) {
+      const int g = e / n_valid, col = e - g * n_valid;
+      const long long orow = static_cast<long long>(row0) / p.pool + g;
+      if (orow * p.pool >= p.M) continue;
+      const float *t = tile + (g * p.pool) * ldt + col;
+      float mx = t[0];
+      for (int q = 1; q < p.pool; ++q) mx = fmaxf(mx, t[q * ldt]);
+      p.Y[orow * p.ldy + col_base + col] = mx;
+    }
+  } else if (!LN_EPI) {
     const bool vec = (p.ldy % 4 == 0) && (n_valid % 4 == 0) && (col_base % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
     if (vec) {
@@ -348,23 +403,29 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   BD_REQUIRE(smem <= 224 * 1024, "bd_linear_tc: tiling needs %zu bytes of shared memory (> 224 KB)", smem);
   static thread_local bool configured = false;
   if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
     configured = true;
   }
   const int n_groups = bd::ceil_div(p.N, NC);
   BD_REQUIRE(n_groups <= 65535, "bd_linear_tc: N too large");
   dim3 grid(bd::ceil_div(p.M, TC_BM), n_groups);
-  if (ln && p.A2)
-    linear_tc_kernel<true, true><<<grid, TC_THREADS, smem, stream>>>(p);
+  if (p.g_idx)
+    linear_tc_kernel<0, 2><<<grid, TC_THREADS, smem, stream>>>(p);
+  else if (p.pool > 0)
+    linear_tc_kernel<2, 0><<<grid, TC_THREADS, smem, stream>>>(p);
+  else if (ln && p.A2)
+    linear_tc_kernel<1, 1><<<grid, TC_THREADS, smem, stream>>>(p);
   else if (ln)
-    linear_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    linear_tc_kernel<1, 0><<<grid, TC_THREADS, smem, stream>>>(p);
   else if (p.A2)
-    linear_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(p);
+    linear_tc_kernel<0, 1><<<grid, TC_THREADS, smem, stream>>>(p);
   else
-    linear_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    linear_tc_kernel<0, 0><<<grid, TC_THREADS, smem, stream>>>(p);
   return BD_OK;
 }
 
@@ -428,5 +489,53 @@ extern "C" int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda
   const int r2 = launch_linear_tc(p, true, bd::as_stream(stream));
   if (r2 != BD_OK) return r2;
   BD_CHECK_LAUNCH("bd_linear_ln_tc");
+  return BD_OK;
+}
+
+// First SharedMLP layer of a set-abstraction level with QueryAndGroup fused into the operand
+// staging (pointnet2_utils.py:334-359 + pytorch_utils.py:25-36): no grouped tensor in HBM.
+// K = C + 3 rounded up to 8; the weight's K columns must be ordered [features | xyz | 0].
+extern "C" int bd_sa_group_linear_tc(const int *idx, const float *feats, int ld_feats, int C, const float *xyz,
+                                     int ld_xyz, const float *new_xyz, int B, int n, int m, int ns, float radius,
+                                     const void *Wp, const float *bias, float *Y, int ldy, int N, int kc, int n_chunks,
+                                     int BN, int n_sub, int split, bd_stream_t stream) {
+  BD_REQUIRE(idx && xyz && new_xyz && Wp && Y && (feats || C == 0), "bd_sa_group_linear_tc: null pointer");
+  BD_REQUIRE(B > 0 && n > 0 && m > 0 && ns > 0 && C >= 0 && N > 0 && ld_xyz >= 3 && ld_feats >= C && ldy >= N,
+             "bd_sa_group_linear_tc: bad sizes");
+  const int K = (C + 3 + 7) / 8 * 8;
+  BD_REQUIRE(kc == KC && n_chunks * KC >= K, "bd_sa_group_linear_tc: KC must be 64 and cover C + 3");
+  BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && n_sub >= 1 && n_sub * BN <= 512 && (split == 1 || split == 3),
+             "bd_sa_group_linear_tc: bad tiling");
+  BD_REQUIRE(static_cast<long long>(B) * m * ns < (1LL << 31), "bd_sa_group_linear_tc: too many rows");
+  LinearTcParams p = {};
+  p.A = xyz;  // unused in gather mode (kept non-null)
+  p.lda = K, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y, p.ldy = ldy;
+  p.M = B * m * ns, p.N = N, p.K = K, p.n_chunks = n_chunks, p.BN = BN, p.n_sub = n_sub, p.relu = 1, p.split = split;
+  p.g_idx = idx, p.g_feat = feats ? feats : xyz, p.g_xyz = xyz, p.g_cen = new_xyz;
+  p.g_ldf = ld_feats, p.g_ldx = ld_xyz, p.g_C = C, p.g_ns = ns, p.g_n = n, p.g_m = m, p.g_inv_r = 1.0f / radius;
+  p.dbg = g_tc_dbg;
+  const int r2 = launch_linear_tc(p, false, bd::as_stream(stream));
+  if (r2 != BD_OK) return r2;
+  BD_CHECK_LAUNCH("bd_sa_group_linear_tc");
+  return BD_OK;
+}
+
+// Last SharedMLP layer of a set-abstraction level with the max-pool over nsample fused into the
+// epilogue (pointnet2_modules.py:251-257): Y (M / pool, N) = max over groups of `pool` rows of
+// relu(A Wᵀ + bias).  pool must divide 128.
+extern "C" int bd_linear_pool_tc(const float *A, int lda, const void *Wp, const float *bias, float *Y, int ldy, int M,
+                                 int N, int K, int kc, int n_chunks, int BN, int n_sub, int pool, int split,
+                                 bd_stream_t stream) {
+  const int rc = check_common(A, Wp, Y, lda, 1, ldy, M, N, K, kc, n_chunks, BN, n_sub, split);
+  if (rc != BD_OK) return rc;
+  BD_REQUIRE(pool > 0 && TC_BM % pool == 0 && M % pool == 0, "bd_linear_pool_tc: pool must divide 128 and M");
+  LinearTcParams p = {};
+  p.A = A, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y, p.lda = lda, p.ldy = ldy;
+  p.M = M, p.N = N, p.K = K, p.n_chunks = n_chunks, p.BN = BN, p.n_sub = n_sub, p.relu = 1, p.split = split;
+  p.pool = pool;
+  p.dbg = g_tc_dbg;
+  const int r2 = launch_linear_tc(p, false, bd::as_stream(stream));
+  if (r2 != BD_OK) return r2;
+  BD_CHECK_LAUNCH("bd_linear_pool_tc");
   return BD_OK;
 }

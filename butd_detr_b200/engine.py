@@ -360,6 +360,8 @@ class ForwardEngine:
         else:
             _lib.call("bd_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), ld_xyz, B, n, m, float(radius), ns,
                       idx.data_ptr())
+        if self.precision != "fp32":
+            return self._sa_level_tc(name, idx, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns)
         kp = self.W[name + ".0"][0].shape[1]
         g = self._empty(B * m * ns, kp)
         _lib.call("bd_group_rows", xyz.data_ptr(), ld_xyz, feats.data_ptr(), ld_feats, C, new_xyz.data_ptr(),
@@ -370,6 +372,40 @@ class ForwardEngine:
         cout = h.shape[1]
         out = self._empty(B, m, cout)
         _lib.call("bd_maxpool_rows", h.data_ptr(), B * m, ns, cout, out.data_ptr())
+        return out
+
+    def _sa_level_tc(self, name, idx, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns):
+        """Tensor-core SA level: [gather fused into layer 0] -> layer 1 -> [layer 2 + max-pool fused]."""
+        if C % 8 == 0 and ld_feats % 4 == 0:
+            # wide feature rows (SA2-4): gather fused into the GEMM's operand staging
+            k0 = name + ".0#gather"
+            if k0 not in self._tc:  # reorder K: [xyz(3) | feats(C)] -> [feats(C) | xyz(3)], pad to 8
+                W, _ = self.W[name + ".0"]
+                Wr = torch.cat([W[:, 3:3 + C], W[:, :3]], 1)
+                self._tc[k0] = pack_weight_tc(torch.nn.functional.pad(Wr, (0, _round_up(C + 3, 8) - (C + 3))), self.split)
+            Wp, (BN, KC, n_chunks, n_sub) = self._tc[k0]
+            b0 = self.W[name + ".0"][1]
+            N0 = b0.shape[0]
+            h = self._empty(B * m * ns, N0)
+            _lib.call("bd_sa_group_linear_tc", idx.data_ptr(), feats.data_ptr(), ld_feats, C, xyz.data_ptr(), ld_xyz,
+                      new_xyz.data_ptr(), B, n, m, ns, float(radius), Wp.data_ptr(), b0.data_ptr(), h.data_ptr(), N0,
+                      N0, KC, n_chunks, BN, n_sub, self.split)
+        else:
+            # SA1 (3 colour channels, 8 floats per grouped row): a streaming gather kernel is cheaper
+            kp = self.W[name + ".0"][0].shape[1]
+            g = self._empty(B * m * ns, kp)
+            _lib.call("bd_group_rows", xyz.data_ptr(), ld_xyz, feats.data_ptr(), ld_feats, C, new_xyz.data_ptr(),
+                      idx.data_ptr(), B, n, m, ns, float(radius), g.data_ptr(), kp)
+            h = self.lin(g, name + ".0", relu=True)
+        h = self.lin(h, name + ".1", relu=True)
+        W2, b2 = self.W[name + ".2"]
+        k2 = name + ".2"
+        if k2 not in self._tc:
+            self._tc[k2] = pack_weight_tc(W2, self.split)
+        Wp2, (BN, KC, n_chunks, n_sub) = self._tc[k2]
+        out = self._empty(B, m, W2.shape[0])
+        _lib.call("bd_linear_pool_tc", h.data_ptr(), h.stride(0), Wp2.data_ptr(), b2.data_ptr(), out.data_ptr(),
+                  W2.shape[0], B * m * ns, W2.shape[0], W2.shape[1], KC, n_chunks, BN, n_sub, ns, self.split)
         return out
 
     def fp_level(self, name, unknown, known, unknown_feats, known_feats, B, n, m):

@@ -152,6 +152,23 @@ int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void 
                  const float *bias, float *Y, int ldy, int M, int N, int K, int KC, int n_chunks,
                  int BN, int n_sub, int relu, int split, bd_stream_t stream);
 
+/* First SharedMLP layer of a set-abstraction level with QueryAndGroup FUSED into the operand
+ * staging (pointnet2_utils.py:334-359 + pytorch_utils.py:25-36): row (b, j, s) of the implicit A is
+ * [ feats[b, idx[b,j,s], 0:C] | (xyz[b, idx] - new_xyz[b, j]) / radius | 0 ], K = round_up(C + 3, 8);
+ * Y (B*m*ns, N) = relu(A Wᵀ + bias).  The packed weight's K columns must be in that order
+ * (features first).  The grouped tensor never exists in HBM. */
+int bd_sa_group_linear_tc(const int *idx, const float *feats, int ld_feats, int C, const float *xyz,
+                          int ld_xyz, const float *new_xyz, int B, int n, int m, int ns,
+                          float radius, const void *Wp, const float *bias, float *Y, int ldy, int N,
+                          int KC, int n_chunks, int BN, int n_sub, int split, bd_stream_t stream);
+
+/* Last SharedMLP layer with the max-pool over nsample fused into the epilogue
+ * (pointnet2_modules.py:251-257): Y (M / pool, N) = max over groups of `pool` consecutive rows of
+ * relu(A Wᵀ + bias); pool divides 128 and M. */
+int bd_linear_pool_tc(const float *A, int lda, const void *Wp, const float *bias, float *Y, int ldy,
+                      int M, int N, int K, int KC, int n_chunks, int BN, int n_sub, int pool,
+                      int split, bd_stream_t stream);
+
 /* Tuning aid: device buffer (>= 64 x int64) that receives clock64() stamps of the phases of CTA
  * (0,0) of every following bd_linear*_tc launch; NULL disables. */
 int bd_linear_tc_set_debug(long long *buf);
