@@ -120,14 +120,14 @@ class Profiler:
     def table(self):
         """[{name, launches, total_ms, mean_ms, share}] sorted by total time (call after a sync)."""
         agg = {}
-        for key, e0, e1 in self.records:
+        for key, args, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            a = agg.setdefault(key, [0, 0.0])
+            a = agg.setdefault(key, [0, 0.0, args])
             a[0] += 1
             a[1] += ms
         total = sum(a[1] for a in agg.values()) or 1.0
-        rows = [{"name": k, "launches": n, "total_ms": t, "mean_ms": t / n, "share": t / total}
-                for k, (n, t) in agg.items()]
+        rows = [{"name": k, "launches": n, "total_ms": t, "mean_ms": t / n, "share": t / total, "args": list(args)}
+                for k, (n, t, args) in agg.items()]
         return sorted(rows, key=lambda r: -r["total_ms"])
 
 
@@ -141,7 +141,7 @@ def call(name, *args):
         rc = getattr(lib, name)(*args, stream_ptr())
         e1.record()
         sizes = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 24))
-        _profiler.records.append((f"{name}{sizes}", e0, e1))
+        _profiler.records.append((f"{name}{sizes}", args, e0, e1))
     else:
         rc = getattr(lib, name)(*args, stream_ptr())
     launch_count += 1

@@ -22,13 +22,23 @@ struct GridMeta {
   int gx, gy, gz, pad;
 };
 
-__global__ void __launch_bounds__(1024) bq_bbox_kernel(const float *__restrict__ xyz, int ld, int n, float radius,
-                                                       GridMeta *__restrict__ meta) {
-  __shared__ float red[6][32];
-  const int b = blockIdx.x;
+// order-preserving float <-> uint mapping, so min / max can use integer atomics
+__device__ __forceinline__ unsigned f2o(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+// partial bounding boxes: grid (BB_PARTS, B); bbox[b] = {min x,y,z, max x,y,z} as ordered uints
+constexpr int BB_PARTS = 32;
+__global__ void __launch_bounds__(256) bq_bbox_kernel(const float *__restrict__ xyz, int ld, int n,
+                                                      unsigned *__restrict__ bbox) {
+  const int b = blockIdx.y;
   xyz += static_cast<long long>(b) * n * ld;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += BB_PARTS * blockDim.x) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float v = __ldg(xyz + static_cast<long long>(i) * ld + c);
@@ -42,30 +52,39 @@ __global__ void __launch_bounds__(1024) bq_bbox_kernel(const float *__restrict__
       mn[c] = fminf(mn[c], __shfl_xor_sync(0xFFFFFFFFu, mn[c], off));
       mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xFFFFFFFFu, mx[c], off));
     }
-    if ((threadIdx.x & 31) == 0) red[c][threadIdx.x >> 5] = mn[c], red[3 + c][threadIdx.x >> 5] = mx[c];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (blockDim.x >> 5); ++w)
-      for (int c = 0; c < 3; ++c) red[c][0] = fminf(red[c][0], red[c][w]), red[3 + c][0] = fmaxf(red[3 + c][0], red[3 + c][w]);
-    // cell edge: slightly larger than the radius (rounding margin), doubled until the grid fits G_MAX
-    float cell = radius * 1.001f;
-    int g[3];
-    for (;;) {
-      long long total = 1;
-      for (int c = 0; c < 3; ++c) {
-        const float ext = fmaxf(red[3 + c][0] - red[c][0], 0.f);
-        g[c] = static_cast<int>(fminf(ext / cell, 1.0e6f)) + 1;
-        total *= g[c];
-      }
-      if (total <= G_MAX) break;
-      cell *= 2.f;
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bbox + b * 8 + c, f2o(mn[c]));
+      atomicMax(bbox + b * 8 + 4 + c, f2o(mx[c]));
     }
-    GridMeta m;
-    m.minx = red[0][0], m.miny = red[1][0], m.minz = red[2][0], m.inv_cell = 1.0f / cell;
-    m.gx = g[0], m.gy = g[1], m.gz = g[2], m.pad = 0;
-    meta[b] = m;
   }
+}
+
+__global__ void bq_bbox_init_kernel(unsigned *__restrict__ bbox, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 8) bbox[i] = (i & 4) ? 0u : 0xFFFFFFFFu;  // max slots start at the smallest key, min slots at the largest
+}
+
+__global__ void bq_meta_kernel(const unsigned *__restrict__ bbox, float radius, GridMeta *__restrict__ meta) {
+  const int b = threadIdx.x;  // one thread per scene (launched <<<1, B>>>, B <= 1024)
+  float lo[3], hi[3];
+  for (int c = 0; c < 3; ++c) lo[c] = o2f(bbox[b * 8 + c]), hi[c] = o2f(bbox[b * 8 + 4 + c]);
+  // cell edge: slightly larger than the radius (rounding margin), doubled until the grid fits G_MAX
+  float cell = radius * 1.001f;
+  int g[3];
+  for (;;) {
+    long long total = 1;
+    for (int c = 0; c < 3; ++c) {
+      const float ext = fmaxf(hi[c] - lo[c], 0.f);
+      g[c] = static_cast<int>(fminf(ext / cell, 1.0e6f)) + 1;
+      total *= g[c];
+    }
+    if (total <= G_MAX) break;
+    cell *= 2.f;
+  }
+  GridMeta m;
+  m.minx = lo[0], m.miny = lo[1], m.minz = lo[2], m.inv_cell = 1.0f / cell;
+  m.gx = g[0], m.gy = g[1], m.gz = g[2], m.pad = 0;
+  meta[b] = m;
 }
 
 __device__ __forceinline__ int cell_coord(float v, float mn, float inv) { return static_cast<int>(floorf((v - mn) * inv)); }
@@ -85,7 +104,8 @@ __global__ void bq_count_kernel(const float *__restrict__ xyz, int ld, int n, co
 }
 
 // exclusive scan of the G_MAX cell counts of one scene (in place: count -> start), cursor = start
-__global__ void __launch_bounds__(1024) bq_scan_kernel(int *__restrict__ count, int *__restrict__ cursor) {
+__global__ void __launch_bounds__(1024) bq_scan_kernel(int *__restrict__ count, int *__restrict__ cursor,
+                                                       const GridMeta *__restrict__ meta) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,7 +113,10 @@ __global__ void __launch_bounds__(1024) bq_scan_kernel(int *__restrict__ count, 
   int *cur = cursor + static_cast<long long>(b) * G_MAX;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int base = 0; base < G_MAX; base += 1024) {
+  const GridMeta gm = meta[b];
+  const int cells = gm.gx * gm.gy * gm.gz;  // cells beyond the grid keep start = total (set below)
+  const int span = (cells + 1023) / 1024 * 1024;
+  for (int base = 0; base < span; base += 1024) {
     const int v = c[base + tid];
     int x = v;
 #pragma unroll
@@ -121,7 +144,8 @@ __global__ void __launch_bounds__(1024) bq_scan_kernel(int *__restrict__ count, 
     if (tid == 1023) carry_s = excl + v;
     __syncthreads();
   }
-  if (tid == 0) c[G_MAX] = carry_s;
+  const int total = carry_s;
+  for (int i = span + tid; i <= G_MAX; i += 1024) c[i] = total;
 }
 
 __global__ void bq_fill_kernel(int n, const int *__restrict__ cell_of, int *__restrict__ cursor,
@@ -225,14 +249,14 @@ bq_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz
 
 extern "C" long long bd_ball_query_grid_workspace_bytes(int B, int n) {
   // meta | count/start (G_MAX+1) | cursor (G_MAX) | cell_of (n) | sorted (n)   per scene, ints
-  return static_cast<long long>(B) * (sizeof(GridMeta) + sizeof(int) * (2LL * G_MAX + 1 + 2LL * n)) + 64;
+  return static_cast<long long>(B) * (sizeof(GridMeta) + sizeof(int) * (2LL * G_MAX + 1 + 2LL * n) + 32) + 64;
 }
 
 extern "C" int bd_ball_query_grid(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m, float radius,
                                   int nsample, int *idx, void *workspace, bd_stream_t stream) {
   BD_REQUIRE(new_xyz && xyz && idx && workspace, "bd_ball_query_grid: null pointer");
   BD_REQUIRE(B > 0 && n > 0 && m > 0 && nsample > 0 && ld_xyz >= 3 && radius > 0.f, "bd_ball_query_grid: bad sizes");
-  BD_REQUIRE(B <= 65535, "bd_ball_query_grid: B too large");
+  BD_REQUIRE(B <= 1024, "bd_ball_query_grid: B too large");
   cudaStream_t s = bd::as_stream(stream);
   unsigned char *ws = static_cast<unsigned char *>(workspace);
   GridMeta *meta = reinterpret_cast<GridMeta *>(ws);
@@ -241,10 +265,13 @@ extern "C" int bd_ball_query_grid(const float *new_xyz, const float *xyz, int ld
   int *cell_of = cursor + static_cast<size_t>(B) * G_MAX;
   int *sorted = cell_of + static_cast<size_t>(B) * n;
   BD_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * static_cast<size_t>(B) * (G_MAX + 1), s), "bd_ball_query_grid");
-  bq_bbox_kernel<<<B, 1024, 0, s>>>(xyz, ld_xyz, n, radius, meta);
+  unsigned *bbox = reinterpret_cast<unsigned *>(sorted + static_cast<size_t>(B) * n);
+  bq_bbox_init_kernel<<<bd::ceil_div(B * 8, 256), 256, 0, s>>>(bbox, B);
+  bq_bbox_kernel<<<dim3(BB_PARTS, B), 256, 0, s>>>(xyz, ld_xyz, n, bbox);
+  bq_meta_kernel<<<1, B, 0, s>>>(bbox, radius, meta);
   dim3 pgrid(bd::ceil_div(n, 256), B);
   bq_count_kernel<<<pgrid, 256, 0, s>>>(xyz, ld_xyz, n, meta, cell_of, count);
-  bq_scan_kernel<<<B, 1024, 0, s>>>(count, cursor);
+  bq_scan_kernel<<<B, 1024, 0, s>>>(count, cursor, meta);
   bq_fill_kernel<<<pgrid, 256, 0, s>>>(n, cell_of, cursor, sorted);
   dim3 qgrid(bd::ceil_div(m, Q_WARPS), B);
   bq_query_kernel<<<qgrid, Q_WARPS * 32, 0, s>>>(new_xyz, xyz, ld_xyz, n, m, radius * radius, nsample, meta, count,

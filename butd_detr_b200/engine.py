@@ -515,7 +515,13 @@ class ForwardEngine:
         B = pc.shape[0]
         ep = {}
         with torch.cuda.device(self.device):
-            vis = self.backbone(pc, ep)  # (B,V,E)
+            if "seed" in ov:  # attention-only entry (BASELINE.json configs[3]): backbone output supplied
+                sd = ov["seed"]
+                vis = sd["features"].contiguous().float()  # (B,V,E) token-major
+                ep["fp2_xyz"], ep["fp2_inds"] = sd["xyz"].contiguous().float(), sd["inds"]
+                ep["fp2_features"] = vis.transpose(1, 2)
+            else:
+                vis = self.backbone(pc, ep)  # (B,V,E)
             V = vis.shape[1]
             vis = vis.reshape(B * V, E)
             ep["seed_inds"], ep["seed_xyz"] = ep["fp2_inds"], ep["fp2_xyz"]
