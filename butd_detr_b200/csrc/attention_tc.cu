@@ -20,12 +20,14 @@
 
 namespace {
 
-constexpr int AT_BM = 128, AT_BK = 128, AT_NV = 48, AT_THREADS = 128, AT_HD = 36;
-constexpr uint32_t QK_PART = 128 * 128;  // 128 rows x 128 B
+constexpr int AT_BM = 128, AT_NV = 48, AT_THREADS = 128, AT_HD = 36;
+constexpr uint32_t QK_PART = 128 * 128;  // Q tile: 128 rows x 128 B
 constexpr uint32_t V_BLK = AT_NV * 128;  // 48 rows x 128 B (one block of 64 keys)
-constexpr uint32_t V_PART = 2 * V_BLK;
-constexpr uint32_t P_BLK = 128 * 128;
-constexpr uint32_t P_PART = 2 * P_BLK;
+constexpr uint32_t P_BLK = 128 * 128;    // 128 rows x 64 keys
+// key-tile width BK (64 or 128 keys): K tile = BK rows x 128 B, V^T / P tiles = BK / 64 blocks
+__host__ __device__ constexpr uint32_t k_part(int BK) { return BK * 128u; }
+__host__ __device__ constexpr uint32_t v_part(int BK) { return (BK / 64) * V_BLK; }
+__host__ __device__ constexpr uint32_t p_part(int BK) { return (BK / 64) * P_BLK; }
 
 struct AttnParams {
   const float *Q, *K, *V;
@@ -34,14 +36,15 @@ struct AttnParams {
   unsigned char *Qp, *Kp, *Vp;  // packed operand tiles (workspace)
   int ldq, ldk, ldv, ldo;
   long long sq_b, sk_b, sv_b, so_b;
-  int Lq, Lk, H, nq, nk;
+  int Lq, Lk, H, nq, nk;  // nk = key tiles of BK keys
   float scale_log2;
 };
 
 // ------------------------------------------------------------------------------------------ pack
 // grid.x = nq + 2 * nk : [0,nq) Q tiles, [nq,nq+nk) K tiles, rest V tiles ; grid.y = H ; grid.z = B
-template <int PARTS>
+template <int PARTS, int BK>
 __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p) {
+  constexpr uint32_t K_PART = k_part(BK), V_PART = v_part(BK);
   const int tid = threadIdx.x;
   const int b = blockIdx.z, h = blockIdx.y;
   int t = blockIdx.x;
@@ -50,11 +53,13 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
     const bool is_q = t < p.nq;
     if (!is_q) t -= p.nq;
     const float *src = is_q ? p.Q + b * p.sq_b : p.K + b * p.sk_b;
-    const int ld = is_q ? p.ldq : p.ldk, n_rows = is_q ? p.Lq : p.Lk, row0 = t * 128;
+    const int tile_rows = is_q ? 128 : BK;
+    const uint32_t part = is_q ? QK_PART : K_PART;
+    const int ld = is_q ? p.ldq : p.ldk, n_rows = is_q ? p.Lq : p.Lk, row0 = t * tile_rows;
     const float mul = is_q ? p.scale_log2 : 1.0f;
     unsigned char *dst = (is_q ? p.Qp + (static_cast<size_t>(b) * p.H + h) * p.nq * (PARTS * QK_PART)
-                               : p.Kp + (static_cast<size_t>(b) * p.H + h) * p.nk * (PARTS * QK_PART)) +
-                         static_cast<size_t>(t) * (PARTS * QK_PART);
+                               : p.Kp + (static_cast<size_t>(b) * p.H + h) * p.nk * (PARTS * K_PART)) +
+                         static_cast<size_t>(t) * (PARTS * part);
     src += h * AT_HD;
     // 128 rows x 8 chunks = 1024 items, 4 per thread, loads batched
     float4 a[4][2];
@@ -63,9 +68,9 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
     for (int it = 0; it < 4; ++it) {
       const int e = tid + it * 256;
       const int r = e & 127, ch = e >> 7;  // consecutive threads -> consecutive rows
-      rr[it] = r, cc[it] = ch;
+      rr[it] = r < tile_rows ? r : -1, cc[it] = ch;
       a[it][0] = a[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < n_rows && ch * 8 < AT_HD) {
+      if (r < tile_rows && row0 + r < n_rows && ch * 8 < AT_HD) {
         const float4 *s = reinterpret_cast<const float4 *>(src + static_cast<long long>(row0 + r) * ld + ch * 8);
         a[it][0] = __ldg(s);
         if (ch * 8 + 4 < AT_HD) a[it][1] = __ldg(s + 1);
@@ -77,20 +82,22 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
                           a[it][1].x * mul, a[it][1].y * mul, a[it][1].z * mul, a[it][1].w * mul};
       uint4 hi, lo;
       tc::split_bf16x8(v, hi, lo);
+      if (rr[it] < 0) continue;
       const uint32_t off = tc::sw128_off(rr[it], cc[it]);
       *reinterpret_cast<uint4 *>(dst + off) = hi;
-      if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + QK_PART + off) = lo;
+      if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + part + off) = lo;
     }
   } else {
     // ---- V^T tile: rows = head dims (48, 36 valid), K = 128 keys in two blocks of 64
     t -= p.nq + p.nk;
     const float *src = p.V + b * p.sv_b + h * AT_HD;
-    const int k0 = t * 128;
+    const int k0 = t * BK;
     unsigned char *dst = p.Vp + ((static_cast<size_t>(b) * p.H + h) * p.nk + t) * (PARTS * V_PART);
-    // 48 rows x 16 key-chunks = 768 items, 3 per thread; item = 8 keys of one head dim
+    // 48 rows x BK/8 key-chunks items (768 for BK = 128), 3 per thread; item = 8 keys of one head dim
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
       const int e = tid + it * 256;
+      if (e >= AT_NV * (BK / 8)) break;
       const int d = e % AT_NV, kc = e / AT_NV;  // consecutive threads -> consecutive head dims (coalesced)
       float v[8];
 #pragma unroll
@@ -108,14 +115,16 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
 }
 
 // ------------------------------------------------------------------------------------------ main
-template <int PARTS>
-__global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnParams p) {
+template <int PARTS, int BK, int STAGES>
+__global__ void __launch_bounds__(AT_THREADS, STAGES == 1 ? 2 : 1) attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr uint32_t KV_STAGE = PARTS * (QK_PART + V_PART);
-  unsigned char *sQ = smem;                     // PARTS * 16 KB
-  unsigned char *sKV = sQ + PARTS * QK_PART;    // 2 stages x (K: PARTS*16 KB, V: PARTS*12 KB)
-  unsigned char *sP = sKV + 2 * KV_STAGE;       // PARTS * 32 KB
+  constexpr uint32_t K_PART = k_part(BK), V_PART = v_part(BK), P_PART = p_part(BK);
+  constexpr uint32_t KV_STAGE = PARTS * (K_PART + V_PART);
+  constexpr int AT_BK = BK;
+  unsigned char *sQ = smem;                       // PARTS * 16 KB
+  unsigned char *sKV = sQ + PARTS * QK_PART;      // STAGES x (K tile | V^T tile)
+  unsigned char *sP = sKV + STAGES * KV_STAGE;
   __shared__ __align__(8) unsigned long long bar_mma, bar_q, bar_kv[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ unsigned char kvalid[AT_BK];
@@ -126,10 +135,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
   const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
   const size_t bh = static_cast<size_t>(b) * p.H + h;
   const unsigned char *Qp = p.Qp + (bh * p.nq + qt) * (PARTS * QK_PART);
-  const unsigned char *Kp = p.Kp + bh * p.nk * (PARTS * QK_PART);
+  const unsigned char *Kp = p.Kp + bh * p.nk * (PARTS * K_PART);
   const unsigned char *Vp = p.Vp + bh * p.nk * (PARTS * V_PART);
 
-  if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 256);
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), AT_BK == 64 ? 128 : 256);
   if (tid == 32) {
     tc::mbar_init(tc::smem_u32(&bar_mma), 1);
     tc::mbar_init(tc::smem_u32(&bar_q), 1);
@@ -141,15 +150,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
-  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + AT_BK;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
 
-  auto issue_kv = [&](int j) {  // thread 0: K and V^T tiles of key tile j -> stage j & 1
-    const uint32_t st = j & 1;
+  auto issue_kv = [&](int j) {  // thread 0: K and V^T tiles of key tile j -> stage j % STAGES
+    const uint32_t st = j % STAGES;
     const uint32_t bar = tc::smem_u32(&bar_kv[st]);
     tc::mbar_arrive_expect_tx(bar, KV_STAGE);
-    tc::bulk_g2s(tc::smem_u32(sKV + st * KV_STAGE), Kp + static_cast<size_t>(j) * (PARTS * QK_PART), PARTS * QK_PART, bar);
-    tc::bulk_g2s(tc::smem_u32(sKV + st * KV_STAGE + PARTS * QK_PART), Vp + static_cast<size_t>(j) * (PARTS * V_PART),
+    tc::bulk_g2s(tc::smem_u32(sKV + st * KV_STAGE), Kp + static_cast<size_t>(j) * (PARTS * K_PART), PARTS * K_PART, bar);
+    tc::bulk_g2s(tc::smem_u32(sKV + st * KV_STAGE + PARTS * K_PART), Vp + static_cast<size_t>(j) * (PARTS * V_PART),
                  PARTS * V_PART, bar);
   };
   if (tid == 0) {
@@ -167,19 +176,23 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
   const int n_tiles = p.nk;
 
   for (int j = 0; j < n_tiles; ++j) {
-    const uint32_t st = j & 1;
+    const uint32_t st = j % STAGES;
     const int k0 = j * AT_BK;
-    // prefetch the next K/V tile into the other stage (its previous MMAs were waited for by
-    // every thread at the end of the last iteration)
-    if (tid == 0 && j + 1 < n_tiles) issue_kv(j + 1);
-    const bool my_valid = (k0 + tid < p.Lk) && !(mask && mask[k0 + tid]);
-    kvalid[tid] = my_valid;
+    // prefetch the next K/V tile into the other stage (its previous MMAs were waited for by every
+    // thread at the end of the last iteration); single-stage: the tile itself is requested here and
+    // a co-resident CTA covers the latency
+    if (tid == 0) {
+      if (STAGES == 2 && j + 1 < n_tiles) issue_kv(j + 1);
+      if (STAGES == 1 && j > 0) issue_kv(j);
+    }
+    const bool my_valid = tid >= AT_BK || ((k0 + tid < p.Lk) && !(mask && mask[k0 + tid]));
+    if (tid < AT_BK) kvalid[tid] = my_valid;
     const bool all_valid = __syncthreads_and(my_valid);  // common case: full, unmasked tile
 
     // ---- S = Q K^T
     if (warp == 0) {
       if (j == 0) tc::mbar_wait(tc::smem_u32(&bar_q), 0);
-      tc::mbar_wait(tc::smem_u32(&bar_kv[st]), (j >> 1) & 1);
+      tc::mbar_wait(tc::smem_u32(&bar_kv[st]), (j / STAGES) & 1);
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t q = tc::smem_u32(sQ), k = tc::smem_u32(sKV + st * KV_STAGE);
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
           tc::mma_bf16(tmem_s, dq, dk, idesc_s, s > 0 ? 1u : 0u);
           if (PARTS == 2) {
             tc::mma_bf16(tmem_s, tc::smem_desc_sw128(q + QK_PART + s * 32), dk, idesc_s, 1u);
-            tc::mma_bf16(tmem_s, dq, tc::smem_desc_sw128(k + QK_PART + s * 32), idesc_s, 1u);
+            tc::mma_bf16(tmem_s, dq, tc::smem_desc_sw128(k + K_PART + s * 32), idesc_s, 1u);
           }
         }
         tc::mma_commit(tc::smem_u32(&bar_mma));
@@ -263,9 +276,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
     if (warp == 0) {
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t pa = tc::smem_u32(sP), va = tc::smem_u32(sKV + st * KV_STAGE + PARTS * QK_PART);
+        const uint32_t pa = tc::smem_u32(sP), va = tc::smem_u32(sKV + st * KV_STAGE + PARTS * K_PART);
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
+        for (int blk = 0; blk < AT_BK / 64; ++blk) {
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             const uint64_t dp = tc::smem_desc_sw128(pa + blk * P_BLK + s * 32);
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
     __syncthreads();  // stage st, the P tile, kvalid and both accumulators are free again
   }
 
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem, AT_BK == 64 ? 128 : 256);
   if (q0 + tid < p.Lq) {
     float *dst = p.O + b * p.so_b + static_cast<long long>(q0 + tid) * p.ldo + h * AT_HD;
     const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
@@ -316,10 +329,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const AttnP
 
 }  // namespace
 
+// tile configuration: bf16x3 -> 64-key tiles, single K/V stage (93 KB: two CTAs per SM overlap each
+// other's softmax / MMA / loads); bf16 -> 128-key tiles, double-buffered (105 KB, also two per SM)
+inline int attn_bk(int split) { return split == 3 ? 64 : 128; }
+
 extern "C" long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int split) {
   const long long parts = split == 3 ? 2 : 1;
-  const long long nq = (Lq + 127) / 128, nk = (Lk + 127) / 128;
-  return static_cast<long long>(B) * H * parts * (nq * QK_PART + nk * (QK_PART + V_PART));
+  const int BK = attn_bk(split);
+  const long long nq = (Lq + 127) / 128, nk = (Lk + BK - 1) / BK;
+  return static_cast<long long>(B) * H * parts * (nq * QK_PART + nk * (k_part(BK) + v_part(BK)));
 }
 
 extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
@@ -334,35 +352,37 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
                  (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
              "bd_attention_tc: Q / K rows and the workspace must be 16-byte aligned");
+  const int BK = attn_bk(split);
   AttnParams p = {};
   p.Q = Q, p.K = K, p.V = V, p.mask = key_padding_mask, p.O = O;
   p.ldq = ldq, p.ldk = ldk, p.ldv = ldv, p.ldo = ldo;
   p.sq_b = sq_b, p.sk_b = sk_b, p.sv_b = sv_b, p.so_b = so_b;
   p.Lq = Lq, p.Lk = Lk, p.H = H;
-  p.nq = bd::ceil_div(Lq, AT_BM), p.nk = bd::ceil_div(Lk, AT_BK);
+  p.nq = bd::ceil_div(Lq, AT_BM), p.nk = bd::ceil_div(Lk, BK);
   p.scale_log2 = scale * 1.4426950408889634f;
   const size_t parts = split == 3 ? 2 : 1;
   unsigned char *ws = static_cast<unsigned char *>(workspace);
   p.Qp = ws;
   p.Kp = p.Qp + static_cast<size_t>(B) * H * p.nq * parts * QK_PART;
-  p.Vp = p.Kp + static_cast<size_t>(B) * H * p.nk * parts * QK_PART;
-  const size_t smem = parts * (QK_PART + 2 * (QK_PART + V_PART) + P_PART) + 1024;
+  p.Vp = p.Kp + static_cast<size_t>(B) * H * p.nk * parts * k_part(BK);
   static thread_local bool configured = false;
   if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024),
             "bd_attention_tc");
-    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024),
             "bd_attention_tc");
     configured = true;
   }
   cudaStream_t s = bd::as_stream(stream);
   dim3 pgrid(p.nq + 2 * p.nk, H, B), grid(p.nq, H, B);
   if (parts == 2) {
-    attention_pack_kernel<2><<<pgrid, 256, 0, s>>>(p);
-    attention_tc_kernel<2><<<grid, AT_THREADS, smem, s>>>(p);
+    const size_t smem = 2 * (QK_PART + (k_part(64) + v_part(64)) + p_part(64)) + 1024;
+    attention_pack_kernel<2, 64><<<pgrid, 256, 0, s>>>(p);
+    attention_tc_kernel<2, 64, 1><<<grid, AT_THREADS, smem, s>>>(p);
   } else {
-    attention_pack_kernel<1><<<pgrid, 256, 0, s>>>(p);
-    attention_tc_kernel<1><<<grid, AT_THREADS, smem, s>>>(p);
+    const size_t smem = QK_PART + 2 * (k_part(128) + v_part(128)) + p_part(128) + 1024;
+    attention_pack_kernel<1, 128><<<pgrid, 256, 0, s>>>(p);
+    attention_tc_kernel<1, 128, 2><<<grid, AT_THREADS, smem, s>>>(p);
   }
   BD_CHECK_LAUNCH("bd_attention_tc");
   return BD_OK;

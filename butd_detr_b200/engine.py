@@ -61,25 +61,27 @@ def _plain(sd, name):
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
 
-def tc_tiling(N, K, split=1, full_rows=False):
+def tc_tiling(N, K, split=1, full_rows=False, wide=False):
     """(BN, KC, n_chunks, n_sub) for bd_linear_tc / bd_linear_ln_tc on an (N, K) weight.
     BN <= 160 columns per accumulator (multiple of 16); a CTA computes n_sub of them (all of
     them when `full_rows`, so that the LayerNorm epilogue sees complete rows); K is consumed in
     chunks of 64 (one 128-byte-swizzle block), zero padded."""
     nt = -(-N // 160)
     BN = _round_up(-(-N // nt), 16)
-    n_sub = nt if full_rows else 1
+    # `wide`: two accumulators per CTA, so the A tile is staged once for 2 x BN columns (measured
+    # 1.3x on 32768-row GEMMs); small-M calls keep one per CTA for more CTAs in flight
+    n_sub = nt if full_rows else (min(nt, 2) if wide else 1)
     n_chunks = -(-K // TC_KC)
     return BN, TC_KC, n_chunks, n_sub
 
 
-def pack_weight_tc(W, split=1, full_rows=False):
+def pack_weight_tc(W, split=1, full_rows=False, wide=False):
     """(N, K) fp32 -> bf16 blocks in the tensor-core kernels' shared-memory layout (128-byte
     swizzle, K-major; csrc/tc_common.cuh): Wp[n_group][k_chunk][part][sub][BN rows][64 k] where
     the 16-byte chunk j of row r holds k-chunk (j ^ (r % 8)); zero padded; part = {hi} or, for
     split 3, {hi, lo} with lo = bf16(W - hi)."""
     N, K = W.shape
-    BN, KC, n_chunks, n_sub = tc_tiling(N, K, split, full_rows)
+    BN, KC, n_chunks, n_sub = tc_tiling(N, K, split, full_rows, wide)
     ng = -(-N // (BN * n_sub))
     Wp = W.new_zeros(ng * n_sub * BN, n_chunks * KC)
     Wp[:N, :K] = W
@@ -231,9 +233,11 @@ class ForwardEngine:
         tc_ok = (N >= 16 and K % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and
                  (add is None or (add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0)))
         if self.precision != "fp32" and tc_ok:  # tensor cores; 1-/3-wide heads and K = 3 / 6 inputs stay fp32
-            if key not in self._tc:
-                self._tc[key] = pack_weight_tc(W, self.split)
-            Wp, (BN, KC, n_chunks, n_sub) = self._tc[key]
+            wide = M >= 4096 and N > 160
+            tkey = key + "#wide" if wide else key
+            if tkey not in self._tc:
+                self._tc[tkey] = pack_weight_tc(W, self.split, wide=wide)
+            Wp, (BN, KC, n_chunks, n_sub) = self._tc[tkey]
             _lib.call("bd_linear_tc", x.data_ptr(), x.stride(0), _lib.ptr(add), lda2, Wp.data_ptr(), _lib.ptr(b),
                       out.data_ptr(), out.stride(0), M, N, K, KC, n_chunks, BN, n_sub, int(relu), self.split)
         else:
