@@ -403,9 +403,9 @@ class ForwardEngine:
             h = self.lin(g, name + ".0", relu=True)
         h = self.lin(h, name + ".1", relu=True)
         W2, b2 = self.W[name + ".2"]
-        k2 = name + ".2"
+        k2 = name + ".2#wide"
         if k2 not in self._tc:
-            self._tc[k2] = pack_weight_tc(W2, self.split)
+            self._tc[k2] = pack_weight_tc(W2, self.split, wide=True)
         Wp2, (BN, KC, n_chunks, n_sub) = self._tc[k2]
         out = self._empty(B, m, W2.shape[0])
         _lib.call("bd_linear_pool_tc", h.data_ptr(), h.stride(0), Wp2.data_ptr(), b2.data_ptr(), out.data_ptr(),
