@@ -52,7 +52,8 @@ _SIGNATURES = {
 }
 
 EXPORTED = sorted(list(_SIGNATURES) + ["bd_version", "bd_last_error", "bd_arch", "bd_fps_resident_capacity",
-                                            "bd_attention_tc_workspace_bytes", "bd_ball_query_grid_workspace_bytes"])
+                                            "bd_attention_tc_workspace_bytes", "bd_ball_query_grid_workspace_bytes",
+                                            "bd_attention_tc_select"])
 
 _lib = None
 launch_count = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
@@ -80,6 +81,8 @@ def load():
     lib.bd_ball_query_grid_workspace_bytes.argtypes = [_I, _I]
     lib.bd_attention_tc_workspace_bytes.restype = _LL
     lib.bd_attention_tc_workspace_bytes.argtypes = [_I, _I, _I, _I, _I]
+    lib.bd_attention_tc_select.restype = _I
+    lib.bd_attention_tc_select.argtypes = [_I]
     _lib = lib
     return lib
 

@@ -38,6 +38,7 @@ struct AttnParams {
   long long sq_b, sk_b, sv_b, so_b;
   int Lq, Lk, H, nq, nk;  // nk = key tiles of BK keys
   float scale_log2;
+  int dbg;  // timing experiments only (bit 0: no softmax arithmetic, bit 1: no P.V MMAs, bit 2: no Q.K^T MMAs)
 };
 
 // ------------------------------------------------------------------------------------------ pack
@@ -103,7 +104,9 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int key = k0 + kc * 8 + i;
-        v[i] = (d < AT_HD && key < p.Lk) ? __ldg(src + static_cast<long long>(key) * p.ldv + d) : 0.f;
+        // row AT_HD of V^T is all ones: column AT_HD of P.V is then the row sum of P (the softmax
+        // denominator comes out of the tensor core with the numerator)
+        v[i] = (d < AT_HD && key < p.Lk) ? __ldg(src + static_cast<long long>(key) * p.ldv + d) : (d == AT_HD ? 1.f : 0.f);
       }
       uint4 hi, lo;
       tc::split_bf16x8(v, hi, lo);
@@ -327,15 +330,300 @@ __global__ void __launch_bounds__(AT_THREADS, STAGES == 1 ? 2 : 1) attention_tc_
   }
 }
 
+
+// ------------------------------------------------------------------ warp-specialised main kernel
+// One CTA = 256 queries (two 128-row tiles) x 1 head x 1 scene, 12 warps:
+//   warp 0      loader: cp.async.bulk of the Q tiles, then the K and V^T tiles of every 128-key
+//               tile through two 2-stage rings (full / empty mbarriers)
+//   warp 1      MMA issuer (one elected lane): S_t = Q_t.K^T into TMEM, Ot_t = P_t.V with the A
+//               operand P_t read FROM TMEM (tcgen05.mma .ts form) — the probabilities never
+//               touch shared memory
+//   warps 4-7   softmax of query tile 0, warps 8-11 of query tile 1 (thread = query row = TMEM
+//               lane).  S_t is read from TMEM, exponentiated, split into bf16 hi / lo and stored
+//               back IN PLACE over the scores it came from (32 fp32 columns -> 16 hi + 16 lo
+//               columns); the tile's P.V result is folded into the register accumulator one
+//               iteration later, when the tensor pipe has long finished it.
+// While one tile's warps do their softmax the tensor pipe runs the other tile's two MMAs
+// (ping-pong), so MUFU / FMA work and tensor work overlap inside one CTA.
+// TMEM columns: [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,304) Ot_0, [320,368) Ot_1.
+constexpr int WS_THREADS = 384, WS_BK = 128;
+
+// second softmax pass over one 128-key score row held in TMEM (see attention_ws_kernel)
+template <int PARTS, bool MASKED>
+__device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long neg_m2, const uint32_t (&vw)[4], bool dead) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t a[32], o[32];
+    tc::tmem_ld32(tS + c * 32, a);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float x0 = __uint_as_float(a[i]), x1 = __uint_as_float(a[i + 1]);
+      tc::add_f32x2(x0, x1, neg_m2);
+      float p0 = tc::ex2_approx(x0), p1 = tc::ex2_approx(x1);
+      if (MASKED) {
+        if (dead || !((vw[c] >> i) & 1u)) p0 = 0.f;
+        if (dead || !((vw[c] >> (i + 1)) & 1u)) p1 = 0.f;
+      }
+      if (PARTS == 2) {
+        tc::split_bf16x2(p0, p1, o[i >> 1], o[16 + (i >> 1)]);
+      } else {
+        o[i >> 1] = tc::pack_bf16x2(p0, p1);
+      }
+    }
+    if (PARTS == 2) {
+      tc::tmem_st32(tS + c * 32, o);
+    } else {
+      uint32_t o16[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o16[i] = o[i];
+      tc::tmem_st16(tS + c * 32, o16);
+    }
+  }
+}
+
+template <int PARTS>
+__global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr uint32_t K_PART = k_part(WS_BK), V_PART = v_part(WS_BK);
+  constexpr uint32_t Q_TILE = PARTS * QK_PART, K_TILE = PARTS * K_PART, V_TILE = PARTS * V_PART;
+  unsigned char *sQ = smem;               // 2 query tiles
+  unsigned char *sK = sQ + 2 * Q_TILE;    // 2 stages
+  unsigned char *sV = sK + 2 * K_TILE;    // 2 stages
+  __shared__ __align__(8) unsigned long long bar_q, bar_kf[2], bar_ke[2], bar_vf[2], bar_ve[2], bar_s[2], bar_p[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  const int lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, qt0 = blockIdx.x * 2;
+  const int nt = min(2, p.nq - qt0);  // query tiles of this CTA
+  const int nk = p.nk;
+  const size_t bh = static_cast<size_t>(b) * p.H + h;
+
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+  if (tid == 32) {
+    tc::mbar_init(tc::smem_u32(&bar_q), 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(tc::smem_u32(&bar_kf[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_ke[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_vf[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_ve[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_s[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_p[i]), 128);
+    }
+    tc::fence_mbar_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------ loader
+    if (tc::elect_one()) {
+      const unsigned char *Qp = p.Qp + (bh * p.nq + qt0) * Q_TILE;
+      const unsigned char *Kp = p.Kp + bh * nk * K_TILE;
+      const unsigned char *Vp = p.Vp + bh * nk * V_TILE;
+      tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_q), nt * Q_TILE);
+      tc::bulk_g2s(tc::smem_u32(sQ), Qp, nt * Q_TILE, tc::smem_u32(&bar_q));
+      for (int j = 0; j < nk; ++j) {
+        const int st = j & 1;
+        const uint32_t par = ((j >> 1) - 1) & 1;
+        if (j >= 2) tc::mbar_wait(tc::smem_u32(&bar_ke[st]), par);
+        tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_kf[st]), K_TILE);
+        tc::bulk_g2s(tc::smem_u32(sK + st * K_TILE), Kp + static_cast<size_t>(j) * K_TILE, K_TILE, tc::smem_u32(&bar_kf[st]));
+        if (j >= 2) tc::mbar_wait(tc::smem_u32(&bar_ve[st]), par);
+        tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_vf[st]), V_TILE);
+        tc::bulk_g2s(tc::smem_u32(sV + st * V_TILE), Vp + static_cast<size_t>(j) * V_TILE, V_TILE, tc::smem_u32(&bar_vf[st]));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------------- MMA issuer
+    const uint32_t idesc_s = tc::idesc_bf16(AT_BM, WS_BK), idesc_o = tc::idesc_bf16(AT_BM, AT_NV);
+    tc::mbar_wait(tc::smem_u32(&bar_q), 0);
+    for (int j = 0; j <= nk; ++j) {  // iteration j: P.V of key tile j-1, then Q.K^T of key tile j
+      for (int t = 0; t < nt; ++t) {
+        const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * 64;
+        if (j > 0) {
+          const int jj = j - 1, st = jj & 1;
+          tc::mbar_wait(tc::smem_u32(&bar_p[t]), jj & 1);
+          if (t == 0) tc::mbar_wait(tc::smem_u32(&bar_vf[st]), (jj >> 1) & 1);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            const uint32_t va = tc::smem_u32(sV + st * V_TILE);
+            if (!(p.dbg & 2))
+#pragma unroll
+            for (int s = 0; s < WS_BK / 16; ++s) {  // 16 keys per step: 8 TMEM columns of packed bf16 pairs
+              const uint32_t a_hi = tS + (s >> 1) * 32 + (s & 1) * 8;
+              const uint64_t dv = tc::smem_desc_sw128(va + (s >> 2) * V_BLK + (s & 3) * 32);
+              tc::mma_bf16_ts(tO, a_hi, dv, idesc_o, s > 0 ? 1u : 0u);
+              if (PARTS == 2) {
+                tc::mma_bf16_ts(tO, a_hi + 16, dv, idesc_o, 1u);
+                tc::mma_bf16_ts(tO, a_hi, tc::smem_desc_sw128(va + V_PART + (s >> 2) * V_BLK + (s & 3) * 32), idesc_o, 1u);
+              }
+            }
+            if (t == nt - 1) tc::mma_commit(tc::smem_u32(&bar_ve[st]));
+            if (j == nk) tc::mma_commit(tc::smem_u32(&bar_s[t]));
+          }
+          __syncwarp();
+        }
+        if (j < nk) {
+          const int st = j & 1;
+          if (t == 0) tc::mbar_wait(tc::smem_u32(&bar_kf[st]), (j >> 1) & 1);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            const uint32_t q = tc::smem_u32(sQ + t * Q_TILE), k = tc::smem_u32(sK + st * K_TILE);
+            if (!(p.dbg & 4))
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {  // head_dim 36 -> 48: three K=16 steps (the tile is padded to 64)
+              const uint64_t dq = tc::smem_desc_sw128(q + s * 32), dk = tc::smem_desc_sw128(k + s * 32);
+              tc::mma_bf16(tS, dq, dk, idesc_s, s > 0 ? 1u : 0u);
+              if (PARTS == 2) {
+                tc::mma_bf16(tS, tc::smem_desc_sw128(q + QK_PART + s * 32), dk, idesc_s, 1u);
+                tc::mma_bf16(tS, dq, tc::smem_desc_sw128(k + K_PART + s * 32), idesc_s, 1u);
+              }
+            }
+            tc::mma_commit(tc::smem_u32(&bar_s[t]));
+            if (t == nt - 1) tc::mma_commit(tc::smem_u32(&bar_ke[st]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4 && ((warp - 4) >> 2) < nt) {
+    // ----------------------------------------------------------------------- softmax warps
+    const int t = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_base + t * 128, tO = tmem + lane_base + 256 + t * 64;
+    const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
+    float m_run = -INFINITY, corr_prev = 1.f;
+    float o_acc[40];  // [0,36) output dims, [36] running softmax denominator, rest padding
+#pragma unroll
+    for (int i = 0; i < 40; ++i) o_acc[i] = 0.f;
+
+    auto fold_o = [&]() {  // o_acc = o_acc * corr + Ot (result of the previous key tile)
+      uint32_t a[32], c[8];
+      tc::tmem_ld32(tO, a);
+      tc::tmem_ld8(tO + 32, c);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], corr_prev, __uint_as_float(a[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], corr_prev, __uint_as_float(c[i]));
+    };
+
+    for (int j = 0; j < nk; ++j) {
+      const int k0 = j * WS_BK;
+      // key validity of this tile as four ballot words (bit i of word c = key k0 + 32 c + i)
+      uint32_t vw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      bool all_valid = !mask && k0 + WS_BK <= p.Lk;
+      if (!all_valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int key = k0 + c * 32 + lane;
+          vw[c] = __ballot_sync(0xFFFFFFFFu, key < p.Lk && !(mask && mask[key]));
+        }
+        all_valid = (vw[0] & vw[1] & vw[2] & vw[3]) == 0xFFFFFFFFu;
+      }
+      tc::mbar_wait(tc::smem_u32(&bar_s[t]), j & 1);
+      tc::fence_after_sync();
+      if (j > 0) fold_o();
+      if (p.dbg & 1) {
+        tc::fence_before_sync();
+        tc::mbar_arrive(tc::smem_u32(&bar_p[t]));
+        continue;
+      }
+
+      // ---- pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t a0[32], a1[32];
+        tc::tmem_ld32(tS + c * 32, a0);
+        tc::tmem_ld32(tS + (c + 1) * 32, a1);
+        tc::tmem_ld_wait();
+        if (all_valid) {
+          float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(a0[i]), __uint_as_float(a1[i])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(a0[i + 1]), __uint_as_float(a1[i + 1])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(a0[i + 2]), __uint_as_float(a1[i + 2])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(a0[i + 3]), __uint_as_float(a1[i + 3])));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if ((vw[c] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(a0[i]));
+            if ((vw[c + 1] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(a1[i]));
+          }
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const bool dead = m_new == -INFINITY;  // every key so far is masked
+      const float corr = dead ? 1.f : tc::ex2_approx(m_run - m_new);
+      const float neg_m = dead ? 0.f : -m_new;
+      const unsigned long long neg_m2 = tc::pack_f32x2(neg_m, neg_m);
+
+      // ---- pass 2: p = 2^(s - m), split into bf16 hi / lo, stored over the scores in place
+      if (all_valid) {
+        softmax_pass2<PARTS, false>(tS, neg_m2, vw, dead);
+      } else {
+        softmax_pass2<PARTS, true>(tS, neg_m2, vw, dead);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(tc::smem_u32(&bar_p[t]));
+      corr_prev = corr;
+      m_run = m_new;
+    }
+    tc::mbar_wait(tc::smem_u32(&bar_s[t]), nk & 1);
+    tc::fence_after_sync();
+    fold_o();
+
+    const int q = (qt0 + t) * AT_BM + row;
+    if (q < p.Lq) {
+      float *dst = p.O + b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
+      const float l_run = o_acc[AT_HD];
+      const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
+#pragma unroll
+      for (int d = 0; d < AT_HD; d += 4) {
+        float4 o4 = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
+        if (l_run == 0.f) o4 = make_float4(NAN, NAN, NAN, NAN);
+        *reinterpret_cast<float4 *>(dst + d) = o4;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
-// tile configuration: bf16x3 -> 64-key tiles, single K/V stage (93 KB: two CTAs per SM overlap each
-// other's softmax / MMA / loads); bf16 -> 128-key tiles, double-buffered (105 KB, also two per SM)
-inline int attn_bk(int split) { return split == 3 ? 64 : 128; }
+// Implementation switch (A/B measurements and the parity tests of both kernels): 1 = the
+// warp-specialised kernel above (default), 0 = the first-generation single-role kernel.
+static int g_attn_impl = 1, g_attn_dbg = 0;
+extern "C" int bd_attention_tc_select(int impl) {
+  BD_REQUIRE((impl & 15) == 0 || (impl & 15) == 1, "bd_attention_tc_select: impl must be 0 or 1");
+  g_attn_impl = impl & 15;
+  g_attn_dbg = impl >> 4;  // undocumented: timing experiments (results are garbage when non-zero)
+  return BD_OK;
+}
+
+// key-tile width of the legacy kernel: bf16x3 -> 64-key tiles, single K/V stage (two CTAs per SM);
+// bf16 -> 128-key tiles, double-buffered.  The warp-specialised kernel always uses 128-key tiles.
+inline int attn_bk(int split) { return (g_attn_impl == 0 && split == 3) ? 64 : 128; }
 
 extern "C" long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int split) {
   const long long parts = split == 3 ? 2 : 1;
-  const int BK = attn_bk(split);
+  const int BK = 128;  // upper bound of both tilings
   const long long nq = (Lq + 127) / 128, nk = (Lk + BK - 1) / BK;
   return static_cast<long long>(B) * H * parts * (nq * QK_PART + nk * (k_part(BK) + v_part(BK)));
 }
@@ -352,6 +640,9 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
                  (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
              "bd_attention_tc: Q / K rows and the workspace must be 16-byte aligned");
+  const int impl = g_attn_impl;
+  BD_REQUIRE(impl == 0 || (ldo % 4 == 0 && so_b % 4 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0),
+             "bd_attention_tc: output rows must be 16-byte aligned");
   const int BK = attn_bk(split);
   AttnParams p = {};
   p.Q = Q, p.K = K, p.V = V, p.mask = key_padding_mask, p.O = O;
@@ -360,22 +651,36 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
   p.Lq = Lq, p.Lk = Lk, p.H = H;
   p.nq = bd::ceil_div(Lq, AT_BM), p.nk = bd::ceil_div(Lk, BK);
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.dbg = g_attn_dbg;
   const size_t parts = split == 3 ? 2 : 1;
   unsigned char *ws = static_cast<unsigned char *>(workspace);
   p.Qp = ws;
   p.Kp = p.Qp + static_cast<size_t>(B) * H * p.nq * parts * QK_PART;
   p.Vp = p.Kp + static_cast<size_t>(B) * H * p.nk * parts * k_part(BK);
+  constexpr size_t WS_SMEM1 = 2 * (QK_PART + k_part(128) + v_part(128)) + 1024, WS_SMEM2 = 2 * WS_SMEM1 - 1024;
   static thread_local bool configured = false;
   if (!configured) {
     BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024),
             "bd_attention_tc");
     BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024),
             "bd_attention_tc");
+    BD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1),
+            "bd_attention_tc");
+    BD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2),
+            "bd_attention_tc");
     configured = true;
   }
   cudaStream_t s = bd::as_stream(stream);
-  dim3 pgrid(p.nq + 2 * p.nk, H, B), grid(p.nq, H, B);
-  if (parts == 2) {
+  dim3 pgrid(p.nq + 2 * p.nk, H, B), grid(p.nq, H, B), wgrid(bd::ceil_div(p.nq, 2), H, B);
+  if (impl == 1) {
+    if (parts == 2) {
+      attention_pack_kernel<2, 128><<<pgrid, 256, 0, s>>>(p);
+      attention_ws_kernel<2><<<wgrid, WS_THREADS, WS_SMEM2, s>>>(p);
+    } else {
+      attention_pack_kernel<1, 128><<<pgrid, 256, 0, s>>>(p);
+      attention_ws_kernel<1><<<wgrid, WS_THREADS, WS_SMEM1, s>>>(p);
+    }
+  } else if (parts == 2) {
     const size_t smem = 2 * (QK_PART + (k_part(64) + v_part(64)) + p_part(64)) + 1024;
     attention_pack_kernel<2, 64><<<pgrid, 256, 0, s>>>(p);
     attention_tc_kernel<2, 64, 1><<<grid, AT_THREADS, smem, s>>>(p);

@@ -207,6 +207,10 @@ int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int
                     const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
                     int B, int H, int Lq, int Lk, int hd, float scale, int split, void *workspace,
                     bd_stream_t stream);
+/* Kernel generation used by bd_attention_tc: 1 = warp-specialised (loader / MMA issuer / two
+ * softmax warpgroups, probabilities kept in TMEM; default), 0 = first-generation kernel (kept for
+ * A/B measurements).  Process-wide; not meant to be flipped while launches are in flight. */
+int bd_attention_tc_select(int impl);
 
 /* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n
  * logits, indices of the k largest sigmoid values, descending, ties -> lower index. n <= 4096 */

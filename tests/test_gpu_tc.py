@@ -84,12 +84,14 @@ def test_linear_ln_tc(cuda_lib, M, N, K, add, split):
     torch.testing.assert_close(Y, want, rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("split", [1, 3])
 @pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 1024, False), (2, 80, 1024, False), (2, 1024, 80, True),
                                              (3, 256, 132, True), (1, 32, 16, True), (2, 70, 65, True),
-                                             (1, 256, 256, False)])
-def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split):
+                                             (1, 256, 256, False), (2, 300, 1000, True), (1, 129, 257, False)])
+def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split, impl):
     H, hd = 8, 36
+    cuda_lib.load().bd_attention_tc_select(impl)
     E = H * hd
     g = _g(Lq * 7 + Lk)
     qkv_q = torch.randn(B, Lq, 2 * E, device="cuda", generator=g)  # q lives in a wider fused buffer
@@ -112,5 +114,6 @@ def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split):
     if masked:
         s = s.masked_fill(mask[:, None, None, :], float("-inf"))
     want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    cuda_lib.load().bd_attention_tc_select(1)
     tol = 2e-2 if split == 1 else 1e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)

@@ -22,7 +22,11 @@ for B in (1, 8, 32):
         args = (q.data_ptr(), E, Lq * E, k.data_ptr(), 2 * E, Lk * 2 * E, v.data_ptr(), 2 * E, Lk * 2 * E, None, o.data_ptr(), E, Lq * E, B, H, Lq, Lk, hd, 1 / 6.0)
         t0 = bench(lambda: _lib.call("bd_attention_f32", *args))
         ws = torch.empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, 3), dtype=torch.uint8, device="cuda")
+        _lib.load().bd_attention_tc_select(0)
+        l1 = bench(lambda: _lib.call("bd_attention_tc", *args, 1, ws.data_ptr()))
+        l3 = bench(lambda: _lib.call("bd_attention_tc", *args, 3, ws.data_ptr()))
+        _lib.load().bd_attention_tc_select(1)
         t1 = bench(lambda: _lib.call("bd_attention_tc", *args, 1, ws.data_ptr()))
         t3 = bench(lambda: _lib.call("bd_attention_tc", *args, 3, ws.data_ptr()))
         fl = 4.0 * B * H * Lq * Lk * hd
-        print(f"B={B:2d} {name:13s} Lq={Lq:4d} Lk={Lk:4d} | simt {t0:8.2f} us | tc bf16 {t1:8.2f} us | tc bf16x3 {t3:8.2f} us | {fl/1e9:.3f} GF -> {fl/t3/1e6:.1f} TF/s (x3 useful)")
+        print(f"B={B:2d} {name:13s} Lq={Lq:4d} Lk={Lk:4d} | simt {t0:8.2f} us | gen1 bf16 {l1:8.2f} bf16x3 {l3:8.2f} us | ws bf16 {t1:8.2f} us bf16x3 {t3:8.2f} us | {fl/1e9:.3f} GF -> {fl/t3/1e6:.1f} TF/s useful (x3 MMAs)", flush=True)
