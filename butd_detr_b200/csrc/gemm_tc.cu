@@ -23,8 +23,8 @@
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
-constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int TC_WARPS = 8;                       // producer / epilogue warps
+constexpr int TC_THREADS = (TC_WARPS + 1) * 32;  // + one MMA-issuing warp
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ITEMS = 4;  // staged items (8 consecutive k of one row) per thread and k-chunk
 constexpr int KC = tc::KB;   // k-chunk = one 64-element swizzle block
@@ -47,6 +47,10 @@ struct LinearTcParams {
   long long *dbg;  // optional clock64() stamps of CTA (0,0), thread 0 (tuning aid)
 };
 
+#define TC_STAMP_T(i, t)                                                                          \
+  do {                                                                                            \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == (t)) p.dbg[i] = clock64();  \
+  } while (0)
 #define TC_STAMP(i)                                                                               \
   do {                                                                                            \
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[i] = clock64();    \
@@ -55,14 +59,14 @@ struct LinearTcParams {
 // MODE: 0 = A, 1 = A + A2, 2 = gathered rows (QueryAndGroup).  EPI: 0 = bias/ReLU, 1 = residual + LayerNorm,
 // 2 = bias/ReLU + max-pool over groups of rows.
 template <int EPI, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, MODE == 0 ? 2 : 1) linear_tc_kernel(const LinearTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) linear_tc_kernel(const LinearTcParams p) {
   constexpr bool LN_EPI = EPI == 1;
   constexpr bool HAS_A2 = MODE == 1;
   constexpr bool GATHER = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // swizzle-128B tiles need 1024-byte aligned bases (in the shared address space)
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) unsigned long long bar_w[TC_MAX_STAGES], bar_mma[TC_MAX_STAGES];
+  __shared__ __align__(8) unsigned long long bar_w[TC_MAX_STAGES], bar_a[TC_MAX_STAGES], bar_mma[TC_MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -81,8 +85,10 @@ __global__ void __launch_bounds__(TC_THREADS, MODE == 0 ? 2 : 1) linear_tc_kerne
   if (tid == 32) {
     for (int i = 0; i < TC_MAX_STAGES; ++i) {
       tc::mbar_init(tc::smem_u32(&bar_w[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_a[i]), TC_WARPS);
       tc::mbar_init(tc::smem_u32(&bar_mma[i]), 1);
     }
+    tc::mbar_init(tc::smem_u32(&bar_done), 1);
     tc::fence_mbar_init();
   }
   tc::fence_before_sync();
@@ -155,195 +161,116 @@ __global__ void __launch_bounds__(TC_THREADS, MODE == 0 ? 2 : 1) linear_tc_kerne
     }
   };
 
-  // S-stage ring.  W(c) is requested `S - lag` chunks ahead: at iteration c the stage last used by
-  // chunk c - lag is refilled (after its MMAs retired) with W(c - lag + S); lag = 2 when S >= 3 so
-  // that the barrier waited on belongs to MMAs issued a full iteration earlier.
+  // S-stage ring, three roles decoupled by mbarriers (no CTA-wide barrier in the main loop):
+  //   producers (warps 0-7): wait stage free -> convert + store A(c) -> one arrival per warp on
+  //                          bar_a[stage]
+  //   issuer (warp 8):       wait bar_w / bar_a of chunk c -> MMAs -> tcgen05.commit -> bar_mma[stage]
+  //                          (= stage free).  Issue blocks while the tensor pipe drains its queue, so
+  //                          it must not be a producer warp: staging of chunk c+1 overlaps MMA(c).
   const int S = p.n_stages;
-  const int lag = S >= 3 ? 2 : 1;
-  auto issue_w = [&](int c) {  // thread 0 only
+  auto issue_w = [&](int c) {  // one thread
     const int st = c % S;
     tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_w[st]), w_bytes);
     tc::bulk_g2s(tc::smem_u32(smem + st * stage_bytes + a_bytes),
                  p.Wp + (static_cast<size_t>(ng) * p.n_chunks + c) * (w_bytes / 2), w_bytes, tc::smem_u32(&bar_w[st]));
   };
-  if (tid == 0)
-    for (int c = 0; c < S && c < p.n_chunks; ++c) issue_w(c);
-  issue_loads(0, ra0, rb0);
-  if (p.n_chunks > 1) issue_loads(1, ra1, rb1);
-  // bias -> shared memory (after the operand loads are in flight; the epilogue must not wait on global memory)
-  for (int i = tid; i < n_sub * BN; i += TC_THREADS) {
-    const int col = ng * n_sub * BN + i;
-    bias_s[i] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
-  }
-  TC_STAMP(2);
 
-  auto step = [&](int c, float4 (&ra)[TC_ITEMS][2], float4 (&rb)[TC_ITEMS][2]) {
-    const int st = c % S;
-    unsigned char *sA = smem + st * stage_bytes;
-    // ---- convert + store chunk c (loads issued two iterations ago; the stage's previous MMAs,
-    //      chunk c - S, were observed complete by every thread at iteration c - S + lag)
-#pragma unroll
-    for (int it = 0; it < TC_ITEMS; ++it) {
-      const bool ok = row_ok[it] && (c * KC + k_off[it] < p.K);
-      float v[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w, ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
-      if (HAS_A2) {
-        v[0] += rb[it][0].x, v[1] += rb[it][0].y, v[2] += rb[it][0].z, v[3] += rb[it][0].w;
-        v[4] += rb[it][1].x, v[5] += rb[it][1].y, v[6] += rb[it][1].z, v[7] += rb[it][1].w;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.f;
-      uint4 hi, lo;
-      tc::split_bf16x8(v, hi, lo);
-      *reinterpret_cast<uint4 *>(sA + s_off[it]) = hi;
-      if (parts == 2) *reinterpret_cast<uint4 *>(sA + A_PART + s_off[it]) = lo;
-    }
-    TC_STAMP(4 + 4 * c);
-    if (c + 2 < p.n_chunks) issue_loads(c + 2, ra, rb);  // refill this register set
-    if (c >= lag) {                                       // retire MMA(c - lag), refill its stage
-      const int j = c - lag;
-      tc::mbar_wait(tc::smem_u32(&bar_mma[j % S]), (j / S) & 1);
-      if (tid == 0 && j + S < p.n_chunks) issue_w(j + S);
-    }
-    TC_STAMP(5 + 4 * c);
-    tc::fence_proxy_async_smem();
-    __syncthreads();
-    TC_STAMP(6 + 4 * c);
-    if (warp == 0) {  // warp-uniform branch; one elected lane issues
-      tc::mbar_wait(tc::smem_u32(&bar_w[st]), (c / S) & 1);
+  if (warp == TC_WARPS) {
+    // ------------------------------------ MMA issuer (also requests the first weight blocks)
+    if (lane == 0)
+      for (int c = 0; c < S && c < p.n_chunks; ++c) issue_w(c);
+    for (int c = 0; c < p.n_chunks; ++c) {
+      const int st = c % S;
+      const uint32_t par = (c / S) & 1;
+      tc::mbar_wait(tc::smem_u32(&bar_w[st]), par);
+      TC_STAMP_T(10 + 3 * c, TC_WARPS * 32);
+      tc::mbar_wait(tc::smem_u32(&bar_a[st]), par);
+      TC_STAMP_T(11 + 3 * c, TC_WARPS * 32);
       tc::fence_after_sync();
       if (tc::elect_one()) {
-      const uint32_t a0 = tc::smem_u32(sA), w0 = a0 + a_bytes;
+        const uint32_t a0 = tc::smem_u32(smem + st * stage_bytes), w0 = a0 + a_bytes;
 #pragma unroll
-      for (int s = 0; s < KC / 16; ++s) {
-        const uint64_t da_hi = tc::smem_desc_sw128(a0 + s * 32);
-        const uint64_t da_lo = tc::smem_desc_sw128(a0 + A_PART + s * 32);
-        const uint32_t acc = (c > 0 || s > 0) ? 1u : 0u;
-        for (int sub = 0; sub < n_sub; ++sub) {
-          const uint32_t d = tmem + sub * BN;
-          const uint64_t dw_hi = tc::smem_desc_sw128(w0 + sub * w_blk + s * 32);
-          tc::mma_bf16(d, da_hi, dw_hi, idesc, acc);
-          if (parts == 2) {
-            const uint64_t dw_lo = tc::smem_desc_sw128(w0 + (n_sub + sub) * w_blk + s * 32);
-            tc::mma_bf16(d, da_lo, dw_hi, idesc, 1u);
-            tc::mma_bf16(d, da_hi, dw_lo, idesc, 1u);
+        for (int s = 0; s < KC / 16; ++s) {
+          const uint64_t da_hi = tc::smem_desc_sw128(a0 + s * 32);
+          const uint64_t da_lo = tc::smem_desc_sw128(a0 + A_PART + s * 32);
+          const uint32_t acc = (c > 0 || s > 0) ? 1u : 0u;
+          for (int sub = 0; sub < n_sub; ++sub) {
+            const uint32_t d = tmem + sub * BN;
+            const uint64_t dw_hi = tc::smem_desc_sw128(w0 + sub * w_blk + s * 32);
+            tc::mma_bf16(d, da_hi, dw_hi, idesc, acc);
+            if (parts == 2) {
+              const uint64_t dw_lo = tc::smem_desc_sw128(w0 + (n_sub + sub) * w_blk + s * 32);
+              tc::mma_bf16(d, da_lo, dw_hi, idesc, 1u);
+              tc::mma_bf16(d, da_hi, dw_lo, idesc, 1u);
+            }
           }
         }
-      }
-      tc::mma_commit(tc::smem_u32(&bar_mma[st]));
+        tc::mma_commit(tc::smem_u32(&bar_mma[st]));
+        if (c == p.n_chunks - 1) tc::mma_commit(tc::smem_u32(&bar_done));
       }
       __syncwarp();
-    }
-    TC_STAMP(7 + 4 * c);
-  };
-  for (int c = 0; c < p.n_chunks; c += 2) {
-    step(c, ra0, rb0);
-    if (c + 1 < p.n_chunks) step(c + 1, ra1, rb1);
-  }
-  // all MMAs retire in order: the last commit covers every earlier one
-  {
-    const int last = p.n_chunks - 1;
-    tc::mbar_wait(tc::smem_u32(&bar_mma[last % S]), (last / S) & 1);
-  }
-  tc::fence_after_sync();
-  TC_STAMP(40);
 
-  // ---- epilogue 1: TMEM -> (+bias, ReLU) -> shared tile (row stride NC + 4 floats).
-  // warp w owns TMEM lanes 32*(w%4)..+31; the warpgroups split the 16-column groups.
-  const int NC = n_sub * BN;
-  const int ldt = NC + 4;
-  float *tile = reinterpret_cast<float *>(smem);
-  const int col_base = ng * NC;
-  {
-    const int r = (warp & 3) * 32 + lane;
-    const int n_groups = NC / 16;
-    constexpr int WG = TC_THREADS / 128;
-    const int per = (n_groups + WG - 1) / WG;
-    const int g0 = (warp >> 2) * per, g1 = min(n_groups, g0 + per);
-    const uint32_t tbase = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    for (int g = g0; g < g1; g += 2) {
-      uint32_t acc[2][16];
-      tc::tmem_ld16(tbase + g * 16, acc[0]);
-      if (g + 1 < g1) tc::tmem_ld16(tbase + (g + 1) * 16, acc[1]);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (g + u >= g1) break;
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = __uint_as_float(acc[u][j]) + bias_s[(g + u) * 16 + j];
-          if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
-          o[j] = v;
-        }
-        float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + (g + u) * 16);
-        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-        dst[3] = make_float4(o[12], o[13], o[14], o[15]);
-      }
-    }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, ncols);
-  TC_STAMP(41);
-
-  // ---- epilogue 2: warp-per-row coalesced write-out
-  const int n_valid = min(NC, p.N - col_base);
-  if (EPI == 2) {
-    // max over groups of `pool` consecutive rows (the nsample neighbours of one centre); M % pool == 0
-    const int groups = TC_BM / p.pool;
-    for (int e = tid; e < groups * n_valid; e += TC_THREADS) {
-      const int g = e / n_valid, col = e - g * n_valid;
-      const long long orow = static_cast<long long>(row0) / p.pool + g;
-      if (orow * p.pool >= p.M) continue;
-      const float *t = tile + (g * p.pool) * ldt + col;
-      float mx = t[0];
-      for (int q = 1; q < p.pool; ++q) mx = fmaxf(mx, t[q * ldt]);
-      p.Y[orow * p.ldy + col_base + col] = mx;
-    }
-  } else if (!LN_EPI) {
-    const bool vec = (p.ldy % 4 == 0) && (n_valid % 4 == 0) && (col_base % 4 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    if (vec) {
-      const int f4 = n_valid / 4;
-#pragma unroll 4
-      for (int i = 0; i < TC_BM / TC_WARPS; ++i) {
-        const int r = warp + i * TC_WARPS, gr = row0 + r;
-        if (gr < p.M) {
-          float4 *y = reinterpret_cast<float4 *>(p.Y + static_cast<long long>(gr) * p.ldy + col_base);
-          const float4 *t = reinterpret_cast<const float4 *>(tile + r * ldt);
-          if (lane < f4) y[lane] = t[lane];
-          if (lane + 32 < f4) y[lane + 32] = t[lane + 32];
-          for (int q = lane + 64; q < f4; q += 32) y[q] = t[q];
-        }
-      }
-    } else {
-      for (int r = warp; r < TC_BM; r += TC_WARPS) {
-        const int gr = row0 + r;
-        if (gr >= p.M) break;
-        float *y = p.Y + static_cast<long long>(gr) * p.ldy + col_base;
-        const float *t = tile + r * ldt;
-        for (int q = lane; q < n_valid; q += 32) y[q] = t[q];
-      }
+      TC_STAMP_T(12 + 3 * c, TC_WARPS * 32);
     }
   } else {
-    // LayerNorm(tile + residual): one warp per row, 4 rows per round so that the residual loads of
-    // a round (40 per lane) are all in flight together.  N <= 320: 10 columns per lane.
-    const float inv_n = 1.0f / static_cast<float>(p.N);
-    float gam[10], bet[10];
+    // ------------------------------------------------------------------------------- producers
+    issue_loads(0, ra0, rb0);
+    if (p.n_chunks > 1) issue_loads(1, ra1, rb1);
+    TC_STAMP(2);
+    auto step = [&](int c, float4 (&ra)[TC_ITEMS][2], float4 (&rb)[TC_ITEMS][2]) {
+      const int st = c % S;
+      unsigned char *sA = smem + st * stage_bytes;
+      if (c >= S) {  // the stage's previous tenant, chunk c - S, must have been consumed
+        tc::mbar_wait(tc::smem_u32(&bar_mma[st]), ((c / S) - 1) & 1);
+        if (tid == 0) issue_w(c);  // refills come from a producer: MMA issue blocks the issuing warp
+        TC_STAMP(30 + c);
+      }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const int col = lane + i * 32;
-      gam[i] = col < p.N ? __ldg(p.gamma + col) : 0.f;
-      bet[i] = col < p.N ? __ldg(p.beta + col) : 0.f;
+      for (int it = 0; it < TC_ITEMS; ++it) {
+        const bool ok = row_ok[it] && (c * KC + k_off[it] < p.K);
+        float v[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w, ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
+        if (HAS_A2) {
+          v[0] += rb[it][0].x, v[1] += rb[it][0].y, v[2] += rb[it][0].z, v[3] += rb[it][0].w;
+          v[4] += rb[it][1].x, v[5] += rb[it][1].y, v[6] += rb[it][1].z, v[7] += rb[it][1].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.f;
+        uint4 hi, lo;
+        tc::split_bf16x8(v, hi, lo);
+        *reinterpret_cast<uint4 *>(sA + s_off[it]) = hi;
+        if (parts == 2) *reinterpret_cast<uint4 *>(sA + A_PART + s_off[it]) = lo;
+      }
+      if (c + 2 < p.n_chunks) issue_loads(c + 2, ra, rb);  // refill this register set
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_a[st]));
+      TC_STAMP(4 + c);
+    };
+    for (int c = 0; c < p.n_chunks; c += 2) {
+      step(c, ra0, rb0);
+      if (c + 1 < p.n_chunks) step(c + 1, ra1, rb1);
     }
-    for (int r0 = warp; r0 < TC_BM; r0 += TC_WARPS * 4) {
-      float x[4][10];
+    // bias -> shared memory while the last MMAs run
+    for (int i = tid; i < n_sub * BN; i += TC_WARPS * 32) {
+      const int col = ng * n_sub * BN + i;
+      bias_s[i] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+    }
+    const int NC = n_sub * BN;
+    const int col_base = ng * NC;
+    const int n_valid = min(NC, p.N - col_base);
+    const int ldt = NC + 4;
+    float *tile = reinterpret_cast<float *>(smem);
+
+    // LayerNorm epilogue: one warp per row, lane owns columns lane + 32 i (N <= 320), LN_ROWS rows
+    // per round.  The residual rows of round 0 are requested now, before the accumulator is
+    // ready, and those of round k + 1 while round k is reduced: their latency is off the path.
+    constexpr int LN_ROWS = 4, LN_ROUNDS = TC_BM / (TC_WARPS * LN_ROWS);
+    float gam[LN_EPI ? 10 : 1], bet[LN_EPI ? 10 : 1], xa[LN_EPI ? LN_ROWS : 1][10], xb[LN_EPI ? LN_ROWS : 1][10];
+    auto ln_load = [&](int round, float (&x)[LN_EPI ? LN_ROWS : 1][10]) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u * TC_WARPS, gr = row0 + r;
-        const bool rok = r < TC_BM && gr < p.M;
+      for (int u = 0; u < LN_ROWS; ++u) {
+        const int r = warp + (round * LN_ROWS + u) * TC_WARPS, gr = row0 + r;
+        const bool rok = gr < p.M;
         const float *res = p.R + (rok ? static_cast<long long>(gr) * p.ldr : 0);
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
@@ -351,64 +278,165 @@ __global__ void __launch_bounds__(TC_THREADS, MODE == 0 ? 2 : 1) linear_tc_kerne
           x[u][i] = (rok && col < p.N) ? __ldg(res + col) : 0.f;
         }
       }
+    };
+    if (LN_EPI) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u * TC_WARPS, gr = row0 + r;
-        if (r >= TC_BM || gr >= p.M) continue;
-        float sum = 0.f;
+      for (int i = 0; i < 10; ++i) {
+        const int col = lane + i * 32;
+        gam[i] = col < p.N ? __ldg(p.gamma + col) : 0.f;
+        bet[i] = col < p.N ? __ldg(p.beta + col) : 0.f;
+      }
+      ln_load(0, xa);
+    }
+
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // producers only: bias_s visible
+    tc::mbar_wait(tc::smem_u32(&bar_done), 0);       // every MMA (and weight copy) has retired:
+    tc::fence_after_sync();                          // the pipeline stages become the output tile
+    TC_STAMP(40);
+
+    // ---- epilogue 1: TMEM -> (+bias, ReLU) -> shared tile (row stride NC + 4 floats).  Thread =
+    //      accumulator row = TMEM lane; the two warpgroups split the 16-column groups.
+    {
+      const int r = (warp & 3) * 32 + lane;
+      const uint32_t tbase = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      const int n_groups = NC / 16;
+      const int per = (n_groups + 1) / 2;
+      const int g0 = (warp >> 2) * per, g1 = min(n_groups, g0 + per);
+      for (int g = g0; g < g1; g += 2) {
+        uint32_t acc[2][16];
+        tc::tmem_ld16(tbase + g * 16, acc[0]);
+        if (g + 1 < g1) tc::tmem_ld16(tbase + (g + 1) * 16, acc[1]);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int col = lane + i * 32;
-          if (col < p.N) x[u][i] += tile[r * ldt + col];
-          sum += x[u][i];
-        }
+        for (int u = 0; u < 2; ++u) {
+          if (g + u >= g1) break;
+          float o[16];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
-        const float mean = sum * inv_n;
-        float sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int col = lane + i * 32;
-          const float d = col < p.N ? x[u][i] - mean : 0.f;
-          sq = fmaf(d, d, sq);
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
-        const float rstd = rsqrtf(sq * inv_n + p.eps);
-        float *y = p.Y + static_cast<long long>(gr) * p.ldy;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int col = lane + i * 32;
-          if (col < p.N) y[col] = (x[u][i] - mean) * rstd * gam[i] + bet[i];
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(acc[u][j]) + bias_s[(g + u) * 16 + j];
+            if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
+            o[j] = v;
+          }
+          float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + (g + u) * 16);
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+          dst[3] = make_float4(o[12], o[13], o[14], o[15]);
         }
       }
     }
+    if (EPI == 0) tc::fence_proxy_async_smem();  // the tile is read by bulk stores (async proxy)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    TC_STAMP(41);
+
+    // ---- epilogue 2: write-out
+    if (EPI == 2) {
+      // max over groups of `pool` consecutive rows (the nsample neighbours of one centre); M % pool == 0
+      const int groups = TC_BM / p.pool;
+      for (int e = tid; e < groups * n_valid; e += TC_WARPS * 32) {
+        const int g = e / n_valid, col = e - g * n_valid;
+        const long long orow = static_cast<long long>(row0) / p.pool + g;
+        if (orow * p.pool >= p.M) continue;
+        const float *t = tile + (g * p.pool) * ldt + col;
+        float mx = t[0];
+        for (int q = 1; q < p.pool; ++q) mx = fmaxf(mx, t[q * ldt]);
+        p.Y[orow * p.ldy + col_base + col] = mx;
+      }
+    } else if (EPI == 0) {
+      const bool vec = (p.ldy % 4 == 0) && (n_valid % 4 == 0) && (col_base % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
+      if (vec) {
+        // one bulk store (TMA engine) per row, issued by the row's thread: the warps are done
+        // after the issue, the copies drain asynchronously
+        if (tid < TC_BM && row0 + tid < p.M) {
+          float *y = p.Y + static_cast<long long>(row0 + tid) * p.ldy + col_base;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y),
+                       "r"(tc::smem_u32(tile + tid * ldt)), "r"(n_valid * 4)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      } else {
+        for (int r = warp; r < TC_BM; r += TC_WARPS) {
+          const int gr = row0 + r;
+          if (gr >= p.M) break;
+          float *y = p.Y + static_cast<long long>(gr) * p.ldy + col_base;
+          const float *t = tile + r * ldt;
+          for (int q = lane; q < n_valid; q += 32) y[q] = t[q];
+        }
+      }
+    } else {
+      const float inv_n = 1.0f / static_cast<float>(p.N);
+      auto ln_rows = [&](int round, float (&x)[LN_EPI ? LN_ROWS : 1][10]) {
+#pragma unroll
+        for (int u = 0; u < LN_ROWS; ++u) {
+          const int r = warp + (round * LN_ROWS + u) * TC_WARPS, gr = row0 + r;
+          if (gr >= p.M) continue;
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const int col = lane + i * 32;
+            if (col < p.N) x[u][i] += tile[r * ldt + col];
+            sum += x[u][i];
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+          const float mean = sum * inv_n;
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const int col = lane + i * 32;
+            const float d = col < p.N ? x[u][i] - mean : 0.f;
+            sq = fmaf(d, d, sq);
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
+          const float rstd = rsqrtf(sq * inv_n + p.eps);
+          float *y = p.Y + static_cast<long long>(gr) * p.ldy;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const int col = lane + i * 32;
+            if (col < p.N) y[col] = (x[u][i] - mean) * rstd * gam[i] + bet[i];
+          }
+        }
+      };
+#pragma unroll
+      for (int round = 0; round < LN_ROUNDS; round += 2) {
+        if (round + 1 < LN_ROUNDS) ln_load(round + 1, xb);
+        ln_rows(round, xa);
+        if (round + 2 < LN_ROUNDS) ln_load(round + 2, xa);
+        if (round + 1 < LN_ROUNDS) ln_rows(round + 1, xb);
+      }
+    }
+    TC_STAMP(42);
   }
-  TC_STAMP(42);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
 int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   const int NC = p.n_sub * p.BN;
   const uint32_t parts = p.split == 3 ? 2 : 1;
   const size_t stage = static_cast<size_t>(parts) * (TC_BM + NC) * KC * 2;
-  int stages = static_cast<int>((220 * 1024) / stage);
+  int stages = static_cast<int>((217 * 1024) / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.n_chunks) stages = p.n_chunks;
   BD_REQUIRE(stages >= 1 && (stages >= 2 || p.n_chunks == 1),
-             "bd_linear_tc: a pipeline stage needs %zu bytes of shared memory; two must fit 220 KB", stage);
+             "bd_linear_tc: a pipeline stage needs %zu bytes of shared memory; two must fit 217 KB", stage);
   p.n_stages = stages;
   const size_t pipe = stage * stages;
   const size_t tile = static_cast<size_t>(TC_BM) * (NC + 4) * 4;
   const size_t smem = (pipe > tile ? pipe : tile) + 1024;  // slack: the dynamic base is 1024-aligned by hand
-  BD_REQUIRE(smem <= 224 * 1024, "bd_linear_tc: tiling needs %zu bytes of shared memory (> 224 KB)", smem);
+  BD_REQUIRE(smem <= 218 * 1024, "bd_linear_tc: tiling needs %zu bytes of shared memory (> 218 KB)", smem);
   static thread_local bool configured = false;
   if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
+    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
     configured = true;
   }
   const int n_groups = bd::ceil_div(p.N, NC);
