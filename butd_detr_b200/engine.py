@@ -58,6 +58,7 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
+FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
 
@@ -378,8 +379,33 @@ class ForwardEngine:
         _lib.call("bd_maxpool_rows", h.data_ptr(), B * m, ns, cout, out.data_ptr())
         return out
 
+    def _sa_level_fused(self, name, idx, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns):
+        """Whole SA level in one kernel (bd_sa_mlp_tc); None when the level's shapes do not fit it."""
+        Ws = [self.W[f"{name}.{i}"] for i in range(3)]
+        N = [w.shape[0] for w, _ in Ws]
+        if not (FUSED_SA and 128 % ns == 0 and N[0] in (64, 128) and N[1] in (64, 128) and N[2] in (64, 128, 256)
+                and Ws[1][0].shape[1] == N[0] and Ws[2][0].shape[1] == N[1]):
+            return None
+        key = name + "#fused"
+        if key not in self._tc:  # layer 0: reorder K [xyz(3) | feats(C)] -> [feats(C) | xyz(3)], pad to 8
+            W0 = Ws[0][0]
+            Wr = torch.cat([W0[:, 3:3 + C], W0[:, :3]], 1)
+            Wr = torch.nn.functional.pad(Wr, (0, _round_up(C + 3, 8) - (C + 3)))
+            self._tc[key] = [pack_weight_tc(w, self.split, full_rows=True)[0] for w in (Wr, Ws[1][0], Ws[2][0])]
+        Wp = self._tc[key]
+        out = self._empty(B, m, N[2])
+        _lib.call("bd_sa_mlp_tc", idx.data_ptr(), feats.data_ptr(), ld_feats, C, xyz.data_ptr(), ld_xyz,
+                  new_xyz.data_ptr(), B, n, m, ns, float(radius), Wp[0].data_ptr(), Ws[0][1].data_ptr(), N[0],
+                  Wp[1].data_ptr(), Ws[1][1].data_ptr(), N[1], Wp[2].data_ptr(), Ws[2][1].data_ptr(), N[2],
+                  out.data_ptr(), N[2], self.split)
+        return out
+
     def _sa_level_tc(self, name, idx, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns):
-        """Tensor-core SA level: [gather fused into layer 0] -> layer 1 -> [layer 2 + max-pool fused]."""
+        """Tensor-core SA level: one fused kernel, or (FUSED_SA = False) [gather fused into layer 0]
+        -> layer 1 -> [layer 2 + max-pool fused]."""
+        out = self._sa_level_fused(name, idx, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns)
+        if out is not None:
+            return out
         if C % 8 == 0 and ld_feats % 4 == 0:
             # wide feature rows (SA2-4): gather fused into the GEMM's operand staging
             k0 = name + ".0#gather"

@@ -169,6 +169,17 @@ int bd_linear_pool_tc(const float *A, int lda, const void *Wp, const float *bias
                       int M, int N, int K, int KC, int n_chunks, int BN, int n_sub, int pool,
                       int split, bd_stream_t stream);
 
+/* One whole set-abstraction level in one kernel: QueryAndGroup (as bd_sa_group_linear_tc) ->
+ * SharedMLP of three [1x1 conv + folded BN + ReLU] layers -> max-pool over nsample
+ * (pointnet2_modules.py:243-257).  The hidden activations stay in shared / tensor memory.
+ * Wp0/1/2: packed weights (pack_weight_tc with full_rows tiling; layer 0's K columns ordered
+ * [features | xyz | 0], K = round_up(C + 3, 8)); N0, N1 in {64,128}, N2 in {64,128,256}; nsample
+ * divides 128.  Y (B*m, N2) pooled rows. */
+int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, int C, const float *xyz, int ld_xyz,
+                 const float *new_xyz, int B, int n, int m, int ns, float radius, const void *Wp0,
+                 const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
+                 const float *b2, int N2, float *Y, int ldy, int split, bd_stream_t stream);
+
 /* Tuning aid: device buffer (>= 64 x int64) that receives clock64() stamps of the phases of CTA
  * (0,0) of every following bd_linear*_tc launch; NULL disables. */
 int bd_linear_tc_set_debug(long long *buf);

@@ -117,3 +117,41 @@ def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split, impl):
     cuda_lib.load().bd_attention_tc_select(1)
     tol = 2e-2 if split == 1 else 1e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("B,n,m,ns,C,widths", [(2, 1000, 64, 64, 3, (64, 64, 128)), (2, 777, 33, 32, 3, (64, 64, 64)), (40, 3000, 512, 64, 3, (64, 64, 128)),
+                                               (2, 512, 96, 32, 128, (128, 128, 256)),
+                                               (1, 300, 40, 16, 256, (128, 128, 256)), (3, 200, 24, 16, 8, (64, 128, 64))])
+def test_sa_mlp_tc(cuda_lib, B, n, m, ns, C, widths, split):
+    """Fused QueryAndGroup + 3-layer SharedMLP + max-pool vs the same maths in torch (fp64)."""
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(n + m * 3 + C)
+    pc = torch.randn(B, n, 3 + C, device="cuda", generator=g)  # [xyz | feats] rows, like the (B,N,6) cloud
+    xyz, feats = pc[..., :3], pc[..., 3:]
+    idx = torch.randint(0, n, (B, m, ns), device="cuda", generator=g, dtype=torch.int32)
+    new_xyz = torch.randn(B, m, 3, device="cuda", generator=g)
+    radius = 0.7
+    K = [C + 3, widths[0], widths[1]]
+    Ws = [torch.randn(widths[i], K[i], device="cuda", generator=g) / math.sqrt(K[i]) for i in range(3)]
+    bs = [torch.randn(widths[i], device="cuda", generator=g) * 0.1 for i in range(3)]
+    kp = (C + 3 + 7) // 8 * 8
+    W0 = F.pad(torch.cat([Ws[0][:, 3:], Ws[0][:, :3]], 1), (0, kp - (C + 3)))  # [feats | xyz | 0]
+    Wp = [pack_weight_tc(w, split, full_rows=True)[0] for w in (W0, Ws[1], Ws[2])]
+    out = torch.full((B * m, widths[2]), float("nan"), device="cuda")
+    cuda_lib.call("bd_sa_mlp_tc", idx.data_ptr(), feats.data_ptr(), 3 + C, C, xyz.data_ptr(), 3 + C, new_xyz.data_ptr(),
+                  B, n, m, ns, radius, Wp[0].data_ptr(), bs[0].data_ptr(), widths[0], Wp[1].data_ptr(), bs[1].data_ptr(),
+                  widths[1], Wp[2].data_ptr(), bs[2].data_ptr(), widths[2], out.data_ptr(), widths[2], split)
+    bi = torch.arange(B, device="cuda")[:, None, None]
+    gx = (xyz[bi, idx.long()] - new_xyz[:, :, None, :]) / radius
+    x = torch.cat([gx, feats[bi, idx.long()]], -1).double()  # reference order [xyz | feats]
+    for i in range(3):
+        if split == 1:
+            x = x.float().bfloat16().double()
+            w = Ws[i].bfloat16().double()
+        else:
+            w = Ws[i].double()
+        x = torch.relu(x @ w.T + bs[i].double())
+    want = x.max(2).values.reshape(B * m, -1).float()
+    tol = 3e-2 if split == 1 else 2e-4
+    torch.testing.assert_close(out, want, rtol=tol, atol=tol)
