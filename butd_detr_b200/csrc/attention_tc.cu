@@ -38,6 +38,7 @@ struct AttnParams {
   long long sq_b, sk_b, sv_b, so_b;
   int Lq, Lk, H, nq, nk;  // nk = key tiles of BK keys
   float scale_log2;
+  int skip_q;  // pack kernel: Q tiles are converted inside the attention kernel, start at the K tiles
   int dbg;  // timing experiments only (bit 0: no softmax arithmetic, bit 1: no P.V MMAs, bit 2: no Q.K^T MMAs)
 };
 
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
   constexpr uint32_t K_PART = k_part(BK), V_PART = v_part(BK);
   const int tid = threadIdx.x;
   const int b = blockIdx.z, h = blockIdx.y;
-  int t = blockIdx.x;
+  int t = blockIdx.x + (p.skip_q ? p.nq : 0);
   if (t < p.nq + p.nk) {
     // ---- row tiles (Q or K): item = (row, 16-byte chunk of 8 head dims); chunks 5..7 are padding
     const bool is_q = t < p.nq;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
 
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
   if (tid == 32) {
-    tc::mbar_init(tc::smem_u32(&bar_q), 1);
+    tc::mbar_init(tc::smem_u32(&bar_q), 8);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tc::smem_u32(&bar_kf[i]), 1);
@@ -424,11 +425,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
   if (warp == 0) {
     // ------------------------------------------------------------------------------ loader
     if (tc::elect_one()) {
-      const unsigned char *Qp = p.Qp + (bh * p.nq + qt0) * Q_TILE;
       const unsigned char *Kp = p.Kp + bh * nk * K_TILE;
       const unsigned char *Vp = p.Vp + bh * nk * V_TILE;
-      tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_q), nt * Q_TILE);
-      tc::bulk_g2s(tc::smem_u32(sQ), Qp, nt * Q_TILE, tc::smem_u32(&bar_q));
       for (int j = 0; j < nk; ++j) {
         const int st = j & 1;
         const uint32_t par = ((j >> 1) - 1) & 1;
@@ -494,8 +492,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
         }
       }
     }
-  } else if (warp >= 4 && ((warp - 4) >> 2) < nt) {
+  } else if (warp >= 4) {
     // ----------------------------------------------------------------------- softmax warps
+    // First, while the K / V tiles are in flight: the CTA's own Q rows, fp32 -> bf16 hi / lo
+    // (softmax scale * log2 e folded in) straight into the operand tiles — a Q tile has exactly
+    // one reader, so it never goes through the pack kernel and HBM.  Item = (row, 16-byte chunk
+    // of 8 head dims); chunks 0..5 cover the three K = 16 steps (36 dims, rest zero).
+    {
+      const float *Qg = p.Q + b * p.sq_b + h * AT_HD;
+      for (int e = tid - 128; e < nt * AT_BM * 6; e += 256) {
+        const int rr = e / 6, ch = e - rr * 6;  // rr = row within the CTA's nt * 128 queries
+        const int q = qt0 * AT_BM + rr;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (q < p.Lq && ch * 8 < AT_HD) {
+          const float4 *src = reinterpret_cast<const float4 *>(Qg + static_cast<long long>(q) * p.ldq + ch * 8);
+          const float4 a0 = __ldg(src);
+          v[0] = a0.x * p.scale_log2, v[1] = a0.y * p.scale_log2, v[2] = a0.z * p.scale_log2, v[3] = a0.w * p.scale_log2;
+          if (ch * 8 + 4 < AT_HD) {
+            const float4 a1 = __ldg(src + 1);
+            v[4] = a1.x * p.scale_log2, v[5] = a1.y * p.scale_log2, v[6] = a1.z * p.scale_log2, v[7] = a1.w * p.scale_log2;
+          }
+        }
+        uint4 hi, lo;
+        tc::split_bf16x8(v, hi, lo);
+        unsigned char *dst = sQ + (rr >> 7) * Q_TILE + tc::sw128_off(rr & 127, ch);
+        *reinterpret_cast<uint4 *>(dst) = hi;
+        if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + QK_PART) = lo;
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_q));
+    }
+    if (((warp - 4) >> 2) < nt) {
     const int t = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -599,6 +627,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
         *reinterpret_cast<float4 *>(dst + d) = o4;
       }
     }
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -673,6 +702,8 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
   cudaStream_t s = bd::as_stream(stream);
   dim3 pgrid(p.nq + 2 * p.nk, H, B), grid(p.nq, H, B), wgrid(bd::ceil_div(p.nq, 2), H, B);
   if (impl == 1) {
+    p.skip_q = 1;
+    pgrid.x = 2 * p.nk;
     if (parts == 2) {
       attention_pack_kernel<2, 128><<<pgrid, 256, 0, s>>>(p);
       attention_ws_kernel<2><<<wgrid, WS_THREADS, WS_SMEM2, s>>>(p);
