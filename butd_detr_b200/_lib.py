@@ -21,6 +21,9 @@ _LL = ctypes.c_longlong
 _SIGNATURES = {
     "bd_fps": [_P, _I, _I, _I, _I, _P, _P, _P],
     "bd_fps_set_cluster": [_I],
+    "bd_fps_ordered": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "bd_grid_build": [_P, _I, _I, _I, _F, _P, _P],
+    "bd_ball_query_grid_query": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P],
     "bd_gather_points": [_P, _P, _I, _I, _I, _I, _P, _P],
     "bd_gather_points_grad": [_P, _P, _I, _I, _I, _I, _P, _P],
     "bd_ball_query": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P],
@@ -54,7 +57,7 @@ _SIGNATURES = {
 
 EXPORTED = sorted(list(_SIGNATURES) + ["bd_version", "bd_last_error", "bd_arch", "bd_fps_resident_capacity",
                                             "bd_attention_tc_workspace_bytes", "bd_ball_query_grid_workspace_bytes",
-                                            "bd_attention_tc_select"])
+                                            "bd_attention_tc_select", "bd_grid_order"])
 
 _lib = None
 launch_count = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
@@ -82,6 +85,8 @@ def load():
     lib.bd_ball_query_grid_workspace_bytes.argtypes = [_I, _I]
     lib.bd_attention_tc_workspace_bytes.restype = _LL
     lib.bd_attention_tc_workspace_bytes.argtypes = [_I, _I, _I, _I, _I]
+    lib.bd_grid_order.restype = ctypes.c_void_p
+    lib.bd_grid_order.argtypes = [_P, _I, _I]
     lib.bd_attention_tc_select.restype = _I
     lib.bd_attention_tc_select.argtypes = [_I]
     _lib = lib

@@ -252,30 +252,69 @@ extern "C" long long bd_ball_query_grid_workspace_bytes(int B, int n) {
   return static_cast<long long>(B) * (sizeof(GridMeta) + sizeof(int) * (2LL * G_MAX + 1 + 2LL * n) + 32) + 64;
 }
 
+namespace {
+struct GridWs {
+  GridMeta *meta;
+  int *count, *cursor, *cell_of, *sorted;
+  unsigned *bbox;
+};
+GridWs grid_ws(void *workspace, int B, int n) {
+  unsigned char *ws = static_cast<unsigned char *>(workspace);
+  GridWs g;
+  g.meta = reinterpret_cast<GridMeta *>(ws);
+  g.count = reinterpret_cast<int *>(ws + static_cast<size_t>(B) * sizeof(GridMeta));
+  g.cursor = g.count + static_cast<size_t>(B) * (G_MAX + 1);
+  g.cell_of = g.cursor + static_cast<size_t>(B) * G_MAX;
+  g.sorted = g.cell_of + static_cast<size_t>(B) * n;
+  g.bbox = reinterpret_cast<unsigned *>(g.sorted + static_cast<size_t>(B) * n);
+  return g;
+}
+}  // namespace
+
+// Cell list of B clouds of n points (cells of edge >= radius): the build half of
+// bd_ball_query_grid.  Afterwards bd_grid_order() is the points' indices grouped by cell (x-fastest
+// cell order) — a spatially coherent permutation, also used by bd_fps_ordered.
+extern "C" int bd_grid_build(const float *xyz, int ld_xyz, int B, int n, float radius, void *workspace,
+                             bd_stream_t stream) {
+  BD_REQUIRE(xyz && workspace, "bd_grid_build: null pointer");
+  BD_REQUIRE(B > 0 && B <= 1024 && n > 0 && ld_xyz >= 3 && radius > 0.f, "bd_grid_build: bad sizes");
+  cudaStream_t s = bd::as_stream(stream);
+  const GridWs g = grid_ws(workspace, B, n);
+  BD_CUDA(cudaMemsetAsync(g.count, 0, sizeof(int) * static_cast<size_t>(B) * (G_MAX + 1), s), "bd_grid_build");
+  bq_bbox_init_kernel<<<bd::ceil_div(B * 8, 256), 256, 0, s>>>(g.bbox, B);
+  bq_bbox_kernel<<<dim3(BB_PARTS, B), 256, 0, s>>>(xyz, ld_xyz, n, g.bbox);
+  bq_meta_kernel<<<1, B, 0, s>>>(g.bbox, radius, g.meta);
+  dim3 pgrid(bd::ceil_div(n, 256), B);
+  bq_count_kernel<<<pgrid, 256, 0, s>>>(xyz, ld_xyz, n, g.meta, g.cell_of, g.count);
+  bq_scan_kernel<<<B, 1024, 0, s>>>(g.count, g.cursor, g.meta);
+  bq_fill_kernel<<<pgrid, 256, 0, s>>>(n, g.cell_of, g.cursor, g.sorted);
+  BD_CHECK_LAUNCH("bd_grid_build");
+  return BD_OK;
+}
+
+extern "C" const int *bd_grid_order(void *workspace, int B, int n) {
+  return workspace ? grid_ws(workspace, B, n).sorted : nullptr;
+}
+
+// Query half: `workspace` holds the cell list built by bd_grid_build with the SAME xyz / radius.
+extern "C" int bd_ball_query_grid_query(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
+                                        float radius, int nsample, int *idx, void *workspace, bd_stream_t stream) {
+  BD_REQUIRE(new_xyz && xyz && idx && workspace, "bd_ball_query_grid_query: null pointer");
+  BD_REQUIRE(B > 0 && n > 0 && m > 0 && nsample > 0 && ld_xyz >= 3 && radius > 0.f, "bd_ball_query_grid_query: bad sizes");
+  const GridWs g = grid_ws(workspace, B, n);
+  dim3 qgrid(bd::ceil_div(m, Q_WARPS), B);
+  bq_query_kernel<<<qgrid, Q_WARPS * 32, 0, bd::as_stream(stream)>>>(new_xyz, xyz, ld_xyz, n, m, radius * radius, nsample,
+                                                                      g.meta, g.count, g.sorted, idx);
+  BD_CHECK_LAUNCH("bd_ball_query_grid_query");
+  return BD_OK;
+}
+
 extern "C" int bd_ball_query_grid(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m, float radius,
                                   int nsample, int *idx, void *workspace, bd_stream_t stream) {
   BD_REQUIRE(new_xyz && xyz && idx && workspace, "bd_ball_query_grid: null pointer");
   BD_REQUIRE(B > 0 && n > 0 && m > 0 && nsample > 0 && ld_xyz >= 3 && radius > 0.f, "bd_ball_query_grid: bad sizes");
   BD_REQUIRE(B <= 1024, "bd_ball_query_grid: B too large");
-  cudaStream_t s = bd::as_stream(stream);
-  unsigned char *ws = static_cast<unsigned char *>(workspace);
-  GridMeta *meta = reinterpret_cast<GridMeta *>(ws);
-  int *count = reinterpret_cast<int *>(ws + static_cast<size_t>(B) * sizeof(GridMeta));
-  int *cursor = count + static_cast<size_t>(B) * (G_MAX + 1);
-  int *cell_of = cursor + static_cast<size_t>(B) * G_MAX;
-  int *sorted = cell_of + static_cast<size_t>(B) * n;
-  BD_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * static_cast<size_t>(B) * (G_MAX + 1), s), "bd_ball_query_grid");
-  unsigned *bbox = reinterpret_cast<unsigned *>(sorted + static_cast<size_t>(B) * n);
-  bq_bbox_init_kernel<<<bd::ceil_div(B * 8, 256), 256, 0, s>>>(bbox, B);
-  bq_bbox_kernel<<<dim3(BB_PARTS, B), 256, 0, s>>>(xyz, ld_xyz, n, bbox);
-  bq_meta_kernel<<<1, B, 0, s>>>(bbox, radius, meta);
-  dim3 pgrid(bd::ceil_div(n, 256), B);
-  bq_count_kernel<<<pgrid, 256, 0, s>>>(xyz, ld_xyz, n, meta, cell_of, count);
-  bq_scan_kernel<<<B, 1024, 0, s>>>(count, cursor, meta);
-  bq_fill_kernel<<<pgrid, 256, 0, s>>>(n, cell_of, cursor, sorted);
-  dim3 qgrid(bd::ceil_div(m, Q_WARPS), B);
-  bq_query_kernel<<<qgrid, Q_WARPS * 32, 0, s>>>(new_xyz, xyz, ld_xyz, n, m, radius * radius, nsample, meta, count,
-                                                  sorted, idx);
-  BD_CHECK_LAUNCH("bd_ball_query_grid");
-  return BD_OK;
+  const int rc = bd_grid_build(xyz, ld_xyz, B, n, radius, workspace, stream);
+  if (rc != BD_OK) return rc;
+  return bd_ball_query_grid_query(new_xyz, xyz, ld_xyz, B, n, m, radius, nsample, idx, workspace, stream);
 }

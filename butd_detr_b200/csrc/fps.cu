@@ -20,6 +20,12 @@
 
 namespace {
 
+__device__ unsigned long long g_fps_dbg[32];  // FPS_DEBUG_COUNT: [0] thread sweeps, [1] warp sweeps, [2] thread rounds, [3] warp rounds
+#ifdef FPS_DEBUG_COUNT
+#define FPS_STAMP(i) do { if (blockIdx.x == 0 && tid == 0 && j == 1000) g_fps_dbg[8 + (i)] = clock64(); } while (0)
+#else
+#define FPS_STAMP(i) do { } while (0)
+#endif
 constexpr int FPS_THREADS = 512;
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 constexpr int MSG_BYTES = 24;  // 16-byte + 8-byte st.async per source CTA and round
@@ -82,10 +88,17 @@ __device__ __forceinline__ int rank_to_k(int r, int Q, int log2bs, int N) {
   return k < N ? k : -1;
 }
 
-template <int CLUSTER, int P>
+// ORDERED: the points are taken in the order given by `order` (a permutation of 0..N-1 per scene
+// that keeps spatial neighbours together — the cell-list order of bd_grid_build) instead of rank
+// order.  A thread's P points then sit in a small box, and a round whose new sample lies farther
+// from that box than the thread's largest running distance cannot change any of them: the thread
+// skips its sweep and re-submits its cached candidate.  After the first ~100 samples a few per cent
+// of the threads are active per round, and the kernel is bound by the reduction chain alone.  The
+// result is unchanged: the reduction key still carries the reference's rank of each point.
+template <int CLUSTER, int P, bool ORDERED>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, int N, int m, int log2bs, int Q,
-                    int *__restrict__ idx_out) {
+                    const int *__restrict__ order, int *__restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   float4 *pts = reinterpret_cast<float4 *>(dyn_smem);  // [FPS_THREADS * P] : x, y, z, bits(k)
   __shared__ uint2 wpart[2][FPS_WARPS];
@@ -112,21 +125,65 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
   const int cta_base = static_cast<int>(crank) * FPS_THREADS * P;
   const int base_rank = cta_base + tid * P;
   float px[P], py[P], pz[P], tmin[P];
+  float bx0 = INFINITY, by0 = INFINITY, bz0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY, bz1 = -INFINITY;
+  const int bs_mask = (1 << log2bs) - 1;
+  auto rank_of = [&](int k) -> uint32_t {  // the reference's rank of point k; padding sorts last
+    if (k < 0) return 0xFFFFFFFFu;
+    const uint32_t trev = log2bs ? (__brev(static_cast<uint32_t>(k & bs_mask)) >> (32 - log2bs)) : 0u;
+    return trev * static_cast<uint32_t>(Q) + static_cast<uint32_t>(k >> log2bs);
+  };
+  if (ORDERED) {
+    // positions base_rank .. base_rank + P - 1 of the spatial order; the thread's own P entries
+    // are then sorted by rank (in its private slice of `pts`), so that "first maximum" inside the
+    // thread is the smallest rank, as the key comparison across threads requires
+    order += static_cast<long long>(scene) * N;
+    float4 *mine = pts + tid * P;
+    for (int i = 0; i < P; ++i) {
+      const int k = base_rank + i < N ? __ldg(order + base_rank + i) : -1;
+      float4 e = make_float4(0.f, 0.f, 0.f, __int_as_float(k));
+      if (k >= 0) {
+        const float *p = xyz + static_cast<long long>(k) * ld;
+        e.x = __ldg(p), e.y = __ldg(p + 1), e.z = __ldg(p + 2);
+      }
+      const uint32_t key = rank_of(k);
+      int q = i - 1;
+      while (q >= 0 && rank_of(__float_as_int(mine[q].w)) > key) {
+        mine[q + 1] = mine[q];
+        --q;
+      }
+      mine[q + 1] = e;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    const int k = rank_to_k(base_rank + i, Q, log2bs, N);
+    int k;
     float x = 0.f, y = 0.f, z = 0.f;
+    if (ORDERED) {
+      const float4 e = pts[tid * P + i];
+      x = e.x, y = e.y, z = e.z, k = __float_as_int(e.w);
+    } else {
+      k = rank_to_k(base_rank + i, Q, log2bs, N);
+    }
     bool valid = k >= 0;
     if (valid) {
-      const float *p = xyz + static_cast<long long>(k) * ld;
-      x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+      if (!ORDERED) {
+        const float *p = xyz + static_cast<long long>(k) * ld;
+        x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+      }
       const float mag = bd::sqnorm_ref(x, y, z);
       valid = !(static_cast<double>(mag) <= 1e-3);  // sampling_gpu.cu:105-106 (double compare)
     }
     px[i] = x, py[i] = y, pz[i] = z;
     tmin[i] = valid ? 1e10f : -2.0f;  // -2 never beats the initial best of -1 and min() keeps it
-    pts[tid * P + i] = make_float4(x, y, z, __int_as_float(k));
+    if (!ORDERED) pts[tid * P + i] = make_float4(x, y, z, __int_as_float(k));
+    if (ORDERED && valid) {
+      bx0 = fminf(bx0, x), by0 = fminf(by0, y), bz0 = fminf(bz0, z);
+      bx1 = fmaxf(bx1, x), by1 = fmaxf(by1, y), bz1 = fmaxf(bz1, z);
+    }
   }
+  float best = -1.0f;  // ORDERED: cached across rounds while the thread's points are untouched
+  int bi = 0;
+  uint32_t lo_cached = 0u;
   const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
   float x1 = x0, y1 = y0, z1 = z0;
   if (crank == 0 && tid == 0) idx_out[0] = 0;
@@ -135,24 +192,72 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
   uint32_t phase_bits = 0;
   for (int j = 1; j < m; ++j) {
     const int p = j & 1;
-    float best = -1.0f;
-    int bi = 0;
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      const float d = bd::sqdist_ref(px[i], py[i], pz[i], x1, y1, z1);
-      const float t = fminf(d, tmin[i]);
-      tmin[i] = t;
-      if (t > best) { best = t; bi = i; }
+    FPS_STAMP(0);
+    bool sweep = true;
+    if (ORDERED) {
+      // lower bound of the distance from the new sample to the thread's box; 1e-5 covers the
+      // rounding of both this bound and the kernel's distance expression
+      const float ex = fmaxf(fmaxf(bx0 - x1, x1 - bx1), 0.f), ey = fmaxf(fmaxf(by0 - y1, y1 - by1), 0.f),
+                  ez = fmaxf(fmaxf(bz0 - z1, z1 - bz1), 0.f);
+      const float lb = fmaf(ez, ez, fmaf(ex, ex, ey * ey));
+      sweep = !(lb * 0.99999f > best) || j == 1;
     }
+#if defined(FPS_DEBUG_COUNT) && FPS_DEBUG_COUNT == 1
+    if (ORDERED) {
+      const unsigned any = __ballot_sync(0xFFFFFFFFu, sweep);
+      if (sweep) atomicAdd(&g_fps_dbg[0], 1ull);
+      if (lane == 0) { atomicAdd(&g_fps_dbg[1], any ? 1ull : 0ull); atomicAdd(&g_fps_dbg[3], 1ull); }
+      atomicAdd(&g_fps_dbg[2], 1ull);
+    }
+#endif
+    if (sweep && !ORDERED) {
+      best = -1.0f;
+      bi = 0;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const float d = bd::sqdist_ref(px[i], py[i], pz[i], x1, y1, z1);
+        const float t = fminf(d, tmin[i]);
+        tmin[i] = t;
+        if (t > best) { best = t; bi = i; }
+      }
+    }
+    if (sweep && ORDERED) {
+      // few warps sweep per round, so the sweep is latency- not throughput-bound: the first-maximum
+      // search runs as G independent chains joined by a short tree (left operand wins ties, i.e.
+      // the smaller index — same winner as the sequential scan)
+      constexpr int G = 5, PER = (P + G - 1) / G;
+      float gv[G];
+      int gi[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) gv[g] = -1.0f, gi[g] = 0;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const float d = bd::sqdist_ref(px[i], py[i], pz[i], x1, y1, z1);
+        const float t = fminf(d, tmin[i]);
+        tmin[i] = t;
+        if (t > gv[i / PER]) { gv[i / PER] = t; gi[i / PER] = i; }
+      }
+#pragma unroll
+      for (int st = 1; st < G; st *= 2)
+#pragma unroll
+        for (int g = 0; g + st < G; g += 2 * st)
+          if (gv[g + st] > gv[g]) { gv[g] = gv[g + st]; gi[g] = gi[g + st]; }
+      best = gv[0], bi = gi[0];
+      lo_cached = 0xFFFFFFFFu - rank_of(__float_as_int(pts[tid * P + bi].w));
+    }
+    FPS_STAMP(1);
     const uint32_t hi = best < 0.f ? 0u : __float_as_uint(best) + 1u;
-    const uint32_t lo = 0xFFFFFFFFu - static_cast<uint32_t>(base_rank + bi);
+    const uint32_t lo = ORDERED ? lo_cached : 0xFFFFFFFFu - static_cast<uint32_t>(base_rank + bi);
     const uint32_t whi = __reduce_max_sync(0xFFFFFFFFu, hi);
     const uint32_t wlo = __reduce_max_sync(0xFFFFFFFFu, hi == whi ? lo : 0u);
     if (lane == 0) wpart[p][warp] = make_uint2(whi, wlo);
+    FPS_STAMP(2);
     __syncthreads();
+    FPS_STAMP(3);
     const uint2 w = lane < FPS_WARPS ? wpart[p][lane] : make_uint2(0u, 0u);
     const uint32_t chi = __reduce_max_sync(0xFFFFFFFFu, w.x);
     const uint32_t clo = __reduce_max_sync(0xFFFFFFFFu, w.x == chi ? w.y : 0u);
+    FPS_STAMP(4);
     int k;
     if (CLUSTER == 1) {
       if (chi == 0u) {
@@ -163,7 +268,21 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
       }
       if (tid == 0) idx_out[j] = k;
     } else {
-      if (warp == 0 && lane < CLUSTER) {
+      if (ORDERED) {
+        // the CTA's winner is the one thread whose key equals the reduced key (ranks are unique):
+        // it knows where its point is and sends the CTA's message itself
+        if (hi == chi && lo == clo && (clo != 0u || tid == 0)) {  // clo == 0: a CTA of padding only
+          float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (chi != 0u) c = pts[tid * P + bi];
+#pragma unroll
+          for (int dst = 0; dst < CLUSTER; ++dst) {
+            const uint32_t dbar = mapa_u32(smem_u32(&bars[p]), dst);
+            st_async_v4(mapa_u32(smem_u32(&slotA[p][crank]), dst), chi, clo, __float_as_uint(c.x),
+                        __float_as_uint(c.y), dbar);
+            st_async_v2(mapa_u32(smem_u32(&slotB[p][crank]), dst), __float_as_uint(c.z), __float_as_uint(c.w), dbar);
+          }
+        }
+      } else if (warp == 0 && lane < CLUSTER) {
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (chi != 0u) c = pts[(0xFFFFFFFFu - clo) - cta_base];
         const uint32_t dbar = mapa_u32(smem_u32(&bars[p]), lane);
@@ -171,7 +290,9 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
                     __float_as_uint(c.y), dbar);
         st_async_v2(mapa_u32(smem_u32(&slotB[p][crank]), lane), __float_as_uint(c.z), __float_as_uint(c.w), dbar);
       }
+      FPS_STAMP(5);
       mbar_wait_cluster(smem_u32(&bars[p]), (phase_bits >> p) & 1u);
+      FPS_STAMP(6);
       phase_bits ^= 1u << p;
       const uint4 a = lane < CLUSTER ? slotA[p][lane] : make_uint4(0u, 0u, 0u, 0u);
       const uint32_t ghi = __reduce_max_sync(0xFFFFFFFFu, a.x);
@@ -185,6 +306,7 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
         x1 = __uint_as_float(aa.z), y1 = __uint_as_float(aa.w), z1 = __uint_as_float(bb.x);
         k = static_cast<int>(bb.y);
       }
+      FPS_STAMP(7);
       if (tid == 0) {
         mbar_arrive_expect_tx(smem_u32(&bars[p]), CLUSTER * MSG_BYTES);  // re-arm for round j+2
         if (crank == 0) idx_out[j] = k;
@@ -253,10 +375,10 @@ int ref_opt_n_threads(int work_size) {
   return v;
 }
 
-template <int CLUSTER, int P>
+template <int CLUSTER, int P, bool ORDERED = false>
 cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, int N, int m, int log2bs, int Q,
-                            int *idx, cudaStream_t stream) {
-  auto kern = fps_resident_kernel<CLUSTER, P>;
+                            int *idx, cudaStream_t stream, const int *order = nullptr) {
+  auto kern = fps_resident_kernel<CLUSTER, P, ORDERED>;
   const size_t smem = static_cast<size_t>(FPS_THREADS) * P * sizeof(float4);
   static thread_local bool configured = false;
   if (!configured) {
@@ -280,10 +402,11 @@ cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, xyz, ld, bstride, N, m, log2bs, Q, idx);
+  return cudaLaunchKernelEx(&cfg, kern, xyz, ld, bstride, N, m, log2bs, Q, order, idx);
 }
 
 int g_force_cluster = -1;  // test hook: bd_fps_set_cluster()
+
 
 }  // namespace
 
@@ -292,6 +415,46 @@ extern "C" int bd_fps_resident_capacity(void) { return 16 * FPS_THREADS * 16; }
 // Test / tuning hook: force the cluster size used for large clouds (8 or 16; -1 = automatic).
 extern "C" int bd_fps_set_cluster(int cluster) {
   g_force_cluster = cluster;
+  return BD_OK;
+}
+
+extern "C" int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp, int *idx, bd_stream_t stream_);
+
+extern "C" int bd_fps_debug_counters(unsigned long long *out4) {  // host copy of the FPS_DEBUG_COUNT counters
+  BD_CUDA(cudaMemcpyFromSymbol(out4, g_fps_dbg, sizeof(unsigned long long) * 32), "bd_fps_debug_counters");
+  return BD_OK;
+}
+
+// bd_fps on spatially ordered points (see fps_resident_kernel): `order` (B, N) is a permutation of
+// 0..N-1 per scene that keeps neighbours together, e.g. bd_grid_order() of the cell list that the
+// ball query of the same level needs anyway.  Same indices as bd_fps, bit for bit.  Clouds outside
+// the 4- / 8-CTA-cluster range fall back to bd_fps.
+extern "C" int bd_fps_ordered(const float *xyz, int ld, int B, int N, int m, const int *order, float *tmp, int *idx,
+                              bd_stream_t stream_) {
+  BD_REQUIRE(xyz && idx && order, "bd_fps_ordered: null pointer");
+  BD_REQUIRE(B > 0 && N > 0 && m >= 0 && ld >= 3, "bd_fps_ordered: bad sizes B=%d N=%d m=%d ld=%d", B, N, m, ld);
+  if (m == 0) return BD_OK;
+  const int bs = ref_opt_n_threads(N);
+  int log2bs = 0;
+  while ((1 << log2bs) < bs) ++log2bs;
+  const int Q = (N + bs - 1) / bs;
+  const long long bstride = static_cast<long long>(N) * ld;
+  const long long T = FPS_THREADS;
+  cudaStream_t stream = bd::as_stream(stream_);
+  cudaError_t e;
+  // positions, not ranks, are distributed here: N of them
+  if (N > 4 * T * 13 && N <= 4 * T * 25 && B > 8)
+    e = launch_resident<4, 25, true>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream, order);
+  else if (N > 8 * T * 8 && N <= 8 * T * 13)
+    e = launch_resident<8, 13, true>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream, order);
+  else
+    return bd_fps(xyz, ld, B, N, m, tmp, idx, stream_);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    bd::set_error("bd_fps_ordered: launch failed: %s", cudaGetErrorString(e));
+    return BD_ERR_CUDA;
+  }
+  BD_CHECK_LAUNCH("bd_fps_ordered");
   return BD_OK;
 }
 

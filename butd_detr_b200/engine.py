@@ -58,6 +58,9 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
+ORDERED_FPS = False  # SA1 FPS over the cell-list order with per-thread pruning (bd_fps_ordered): bit-identical, but
+# measured no faster (1.6 % of threads / 13 % of warps sweep per round, yet one lone sweeping warp still takes ~1000
+# cycles per round, as long as the whole un-pruned sweep with 4 warps per scheduler); kept for the tests and DESIGN.md §4
 FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
@@ -375,7 +378,12 @@ class ForwardEngine:
     def sa_level(self, name, xyz, ld_xyz, feats, ld_feats, C, new_xyz, B, n, m, radius, ns):
         """QueryAndGroup + SharedMLP + max-pool (pointnet2_modules.py:243-257), token-major."""
         idx = self._empty(B, m, ns, dtype=torch.int32)
-        if n >= GRID_BALL_QUERY_MIN_POINTS:  # cell-list search (identical output, ~100x fewer distance tests)
+        grid = getattr(self, "_grid", None)
+        if grid is not None and grid[1] == n and grid[2] == float(radius):  # cell list already built (backbone)
+            _lib.call("bd_ball_query_grid_query", new_xyz.data_ptr(), xyz.data_ptr(), ld_xyz, B, n, m, float(radius), ns,
+                      idx.data_ptr(), grid[0].data_ptr())
+            self._grid = None
+        elif n >= GRID_BALL_QUERY_MIN_POINTS:  # cell-list search (identical output, ~100x fewer distance tests)
             ws = self._empty(_lib.load().bd_ball_query_grid_workspace_bytes(B, n), dtype=torch.uint8)
             _lib.call("bd_ball_query_grid", new_xyz.data_ptr(), xyz.data_ptr(), ld_xyz, B, n, m, float(radius), ns,
                       idx.data_ptr(), ws.data_ptr())
@@ -474,7 +482,20 @@ class ForwardEngine:
         main = torch.cuda.current_stream()
         xyz, ld_xyz, n = pc, ld, N
         feats, ld_feats, C = pc[..., 3:], ld, C_in
-        inds1 = self.fps(pc, ld, B, N, SA_CFG[0][1])
+        self._grid = None
+        if ORDERED_FPS and N >= GRID_BALL_QUERY_MIN_POINTS:
+            # the cell list of SA1's ball query is built first: its cell order also drives the
+            # pruned furthest-point sampling (bd_fps_ordered)
+            lib = _lib.load()
+            ws = self._empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8)
+            _lib.call("bd_grid_build", pc.data_ptr(), ld, B, N, float(SA_CFG[0][2]), ws.data_ptr())
+            self._grid = (ws, N, float(SA_CFG[0][2]))
+            inds1 = self._empty(B, SA_CFG[0][1], dtype=torch.int32)
+            tmp = self._empty(B, N) if N > lib.bd_fps_resident_capacity() else None
+            _lib.call("bd_fps_ordered", pc.data_ptr(), ld, B, N, SA_CFG[0][1], lib.bd_grid_order(ws.data_ptr(), B, N),
+                      _lib.ptr(tmp), inds1.data_ptr())
+        else:
+            inds1 = self.fps(pc, ld, B, N, SA_CFG[0][1])
         xyz1 = self.gather_rows(pc, ld, inds1, B, N, SA_CFG[0][1], 3)
         # coordinates of levels 2-4 only depend on xyz: run their (serial) FPS chain on a side
         # stream while the main stream does ball query + MLPs

@@ -54,6 +54,12 @@ const char *bd_arch(void);
  * opt_n_threads(N) threads (cuda_utils.h:20-24). */
 int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp, int *idx, bd_stream_t stream);
 int bd_fps_resident_capacity(void);
+/* bd_fps on spatially ordered points: `order` (B,N) is a permutation of 0..N-1 per scene that keeps
+ * neighbours together (bd_grid_order of the level's cell list).  A thread's points then sit in a
+ * small box and rounds whose new sample is farther away than the box's largest running distance
+ * are skipped for that thread.  Same indices as bd_fps, bit for bit. */
+int bd_fps_ordered(const float *xyz, int ld, int B, int N, int m, const int *order, float *tmp,
+                   int *idx, bd_stream_t stream);
 /* Tuning / test hook: force the cluster size (8 or 16 CTAs) used for clouds that need more than
  * one CTA; -1 restores the automatic choice (16 for B <= 8 scenes, else 8). */
 int bd_fps_set_cluster(int cluster);
@@ -81,6 +87,15 @@ int bd_ball_query(const float *new_xyz, const float *xyz, int ld_xyz, int B, int
 long long bd_ball_query_grid_workspace_bytes(int B, int n);
 int bd_ball_query_grid(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
                        float radius, int nsample, int *idx, void *workspace, bd_stream_t stream);
+/* The two halves of bd_ball_query_grid: bd_grid_build bins the clouds once (cells of edge >=
+ * radius); bd_ball_query_grid_query answers queries against that cell list (same xyz / radius);
+ * bd_grid_order returns the device array (B,n) of point indices grouped by cell. */
+int bd_grid_build(const float *xyz, int ld_xyz, int B, int n, float radius, void *workspace,
+                  bd_stream_t stream);
+const int *bd_grid_order(void *workspace, int B, int n);
+int bd_ball_query_grid_query(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
+                             float radius, int nsample, int *idx, void *workspace,
+                             bd_stream_t stream);
 
 /* group_points(points (B,C,n), idx (B,m,ns)) -> out (B,C,m,ns)   group_points.cpp:17-40 */
 int bd_group_points(const float *points, const int *idx, int B, int C, int n, int m, int ns,

@@ -54,6 +54,25 @@ def test_fps_cluster_sizes_agree(cluster, ext, oracle_lib, cuda_lib):
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("kind,B,N,m", [("room", 2, 50000, 2048), ("room", 10, 50000, 1024), ("lattice", 9, 40000, 700),
+                                        ("dup", 3, 50000, 600), ("uniform", 12, 30000, 512)])
+def test_fps_ordered_equals_fps(cuda_lib, oracle_lib, kind, B, N, m):
+    """bd_fps_ordered (cell-list order + per-thread pruning) returns bd_fps's indices bit for bit
+    (8-CTA clusters for B <= 8, 4-CTA clusters beyond; ties, duplicates, partially empty CTAs)."""
+    lib = cuda_lib.load()
+    xyz = cloud(11 + B, N, kind, B).cuda()
+    want = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    cuda_lib.call("bd_fps", xyz.data_ptr(), 3, B, N, m, None, want.data_ptr())
+    ws = torch.empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8, device="cuda")
+    cuda_lib.call("bd_grid_build", xyz.data_ptr(), 3, B, N, 0.2, ws.data_ptr())
+    got = torch.full((B, m), -1, dtype=torch.int32, device="cuda")
+    cuda_lib.call("bd_fps_ordered", xyz.data_ptr(), 3, B, N, m, lib.bd_grid_order(ws.data_ptr(), B, N), None,
+                  got.data_ptr())
+    assert torch.equal(got, want), f"first mismatch at {(got != want).nonzero()[:3].tolist()}"
+    if B <= 2:
+        assert torch.equal(got.cpu(), oracle_lib.furthest_point_sampling(xyz.cpu(), m))
+
+
 def test_fps_strided_input_matches_contiguous(cuda_lib, oracle_lib):
     """FPS straight from the (B,N,6) point cloud (ld = 6) == FPS on the xyz copy."""
     from butd_detr_b200 import synth
