@@ -307,7 +307,8 @@ def main():
             pk, unit = (peak, "GB/s") if bound == "hbm" else (tensor_peak(), "TFLOP/s")
             ach = units / (r["mean_ms"] * 1e-3) / (1e9 if bound == "hbm" else 1e12)
             rooflines.append({"kernel": r["name"], "bound": bound, "achieved": ach, "peak": pk, "unit": unit,
-                              "frac": ach / pk, "traffic": None, "peak_source": peak_src,
+                              "frac": ach / pk, "traffic": measured_traffic(r["name"].split("(")[0], B),
+                              "peak_source": peak_src,
                               "algorithmic_units_per_launch": units, "mean_launch_ms": r["mean_ms"],
                               "share_of_step": r["share"]})
         roofline = rooflines[0] if rooflines else None  # the dominant kernel (largest share of the step)
@@ -382,7 +383,25 @@ def algorithmic_work(name, a):
         return "tensor", 2.0 * a[6] * a[7] * a[8]
     if name == "bd_sa_group_linear_tc":  # C at 3, B, n, m, ns at 7..10, N at 16
         return "tensor", 2.0 * a[7] * a[9] * a[10] * a[16] * (a[3] + 3)
+    if name == "bd_sa_mlp_tc":  # C at 3, B, n, m, ns at 7..10, N0 / N1 / N2 at 14 / 17 / 20 : the three 1x1 convs
+        return "tensor", 2.0 * a[7] * a[9] * a[10] * ((a[3] + 3) * a[14] + a[14] * a[17] + a[17] * a[20])
+    if name == "bd_fps_ordered":  # xyz, ld, B, N, m
+        return "hbm", a[2] * (12 * a[3] + 4 * a[4])
+    if name == "bd_ball_query_grid_query":  # same arguments as bd_ball_query_grid
+        return "hbm", a[3] * (12 * a[4] + 12 * a[5] + 4 * a[5] * a[7])
     return None
+
+
+def measured_traffic(name, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's dominant kernel
+    from the committed `ncu --set full` capture (profiles/r01_traffic.json: captured at the batch
+    size named there; None when the capture is for another batch size or kernel)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    e = d.get(name)
+    return e["dram_bytes_per_launch"] if e and e.get("batch") == B else None
 
 
 def algorithmic_bytes(kernel, B):
