@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
   constexpr uint32_t K_PART = k_part(BK), V_PART = v_part(BK);
   const int tid = threadIdx.x;
   const int b = blockIdx.z, h = blockIdx.y;
+  bd::pdl_launch_dependents();
+  bd::pdl_wait();  // Q / K / V come from the preceding projection kernels
   int t = blockIdx.x + (p.skip_q ? p.nq : 0);
   if (t < p.nq + p.nk) {
     // ---- row tiles (Q or K): item = (row, 16-byte chunk of 8 head dims); chunks 5..7 are padding
@@ -421,6 +423,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
+  bd::pdl_launch_dependents();
+  bd::pdl_wait();  // packed K / V tiles (pack kernel) and Q rows (projection kernel) are complete
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ loader
@@ -705,11 +709,11 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
     p.skip_q = 1;
     pgrid.x = 2 * p.nk;
     if (parts == 2) {
-      attention_pack_kernel<2, 128><<<pgrid, 256, 0, s>>>(p);
-      attention_ws_kernel<2><<<wgrid, WS_THREADS, WS_SMEM2, s>>>(p);
+      BD_CUDA(bd::launch_pdl(attention_pack_kernel<2, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
+      BD_CUDA(bd::launch_pdl(attention_ws_kernel<2>, wgrid, dim3(WS_THREADS), WS_SMEM2, s, p), "bd_attention_tc");
     } else {
-      attention_pack_kernel<1, 128><<<pgrid, 256, 0, s>>>(p);
-      attention_ws_kernel<1><<<wgrid, WS_THREADS, WS_SMEM1, s>>>(p);
+      BD_CUDA(bd::launch_pdl(attention_pack_kernel<1, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
+      BD_CUDA(bd::launch_pdl(attention_ws_kernel<1>, wgrid, dim3(WS_THREADS), WS_SMEM1, s, p), "bd_attention_tc");
     }
   } else if (parts == 2) {
     const size_t smem = 2 * (QK_PART + (k_part(64) + v_part(64)) + p_part(64)) + 1024;

@@ -46,6 +46,30 @@ int sm_count();
     }                                                                                \
   } while (0)
 
+// ---- programmatic dependent launch (PDL).  The forward is a chain of ~320 short kernels; with PDL
+// a kernel is scheduled as soon as its predecessor in the stream lets it (pdl_launch_dependents, or
+// the predecessor's CTAs leaving their SMs) and runs its prologue — barrier init, TMEM allocation,
+// the bulk copies of its WEIGHTS — under the predecessor's tail.  pdl_wait() then blocks until the
+// predecessor has completed and its writes are visible; every read of activations and every
+// global write of a PDL-launched kernel comes after it.  Only kernels containing pdl_wait() may be
+// launched through launch_pdl().
+extern int g_pdl;  // bd_set_pdl(): 1 = use PDL launches (default), 0 = plain stream order
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

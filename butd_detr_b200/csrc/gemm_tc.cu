@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // provably warp-uniform
+  bd::pdl_launch_dependents();  // the next kernel may start its prologue under this one
   TC_STAMP(0);
   const int row0 = blockIdx.x * TC_BM;
   const int ng = blockIdx.y;  // column group: n_sub consecutive BN-wide tiles
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   // Per-thread staging plan, identical for every k-chunk.  A warp-item covers 8 rows x 4 chunks
   // (lane = chunk_local * 8 + row_local): 128 contiguous bytes per row from global memory and
   // conflict-free 16-byte st.shared into the swizzled tile.
+  if (GATHER) bd::pdl_wait();  // the neighbour indices read below come from the preceding kernel
   long long g_off[TC_ITEMS], g2_off[TC_ITEMS], s_cen[TC_ITEMS];
   uint32_t s_off[TC_ITEMS];
   int k_off[TC_ITEMS];
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
     }
   } else {
     // ------------------------------------------------------------------------------- producers
+    bd::pdl_wait();  // activations (A, A2, gather sources, residual) come from the preceding kernels
     issue_loads(0, ra0, rb0);
     if (p.n_chunks > 1) issue_loads(1, ra1, rb1);
     TC_STAMP(2);
@@ -443,17 +446,17 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   BD_REQUIRE(n_groups <= 65535, "bd_linear_tc: N too large");
   dim3 grid(bd::ceil_div(p.M, TC_BM), n_groups);
   if (p.g_idx)
-    linear_tc_kernel<0, 2><<<grid, TC_THREADS, smem, stream>>>(p);
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 2>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else if (p.pool > 0)
-    linear_tc_kernel<2, 0><<<grid, TC_THREADS, smem, stream>>>(p);
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<2, 0>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else if (ln && p.A2)
-    linear_tc_kernel<1, 1><<<grid, TC_THREADS, smem, stream>>>(p);
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<1, 1>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else if (ln)
-    linear_tc_kernel<1, 0><<<grid, TC_THREADS, smem, stream>>>(p);
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<1, 0>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else if (p.A2)
-    linear_tc_kernel<0, 1><<<grid, TC_THREADS, smem, stream>>>(p);
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 1>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else
-    linear_tc_kernel<0, 0><<<grid, TC_THREADS, smem, stream>>>(p);
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 0>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   return BD_OK;
 }
 

@@ -15,6 +15,8 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+int g_pdl = 1;
+
 int sm_count() {
   static thread_local int n = 0;
   if (n == 0) {
@@ -218,3 +220,10 @@ int bd_add_rows(const float *X1, int ld1, const float *X2, int ld2, float *Y, in
 }
 
 }  // extern "C"
+
+// 1 (default): the tensor-core kernels are launched with programmatic stream serialization (PDL),
+// 0: plain stream order.  Process-wide; set it before capturing a CUDA graph.
+extern "C" int bd_set_pdl(int enabled) {
+  bd::g_pdl = enabled ? 1 : 0;
+  return BD_OK;
+}

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpPar
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
+  bd::pdl_launch_dependents();
 
   // weight chunk t (global numbering over the three layers) -> ring stage t & 1
   auto issue_w = [&](int l, int c, int t) {  // one thread
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpPar
     }
   } else {
     // -------------------------------------------------------------- staging / epilogue warps
+    bd::pdl_wait();  // neighbour indices, features and centres come from the preceding kernels
     // staging plan (same for every k-chunk): a warp-item covers 8 rows x 4 chunks of 8 k
     long long f_off[SA_ITEMS], x_off[SA_ITEMS], c_off[SA_ITEMS];
     uint32_t s_off[SA_ITEMS];
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const Sa
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
+  bd::pdl_launch_dependents();
 
   if (warp == SA_WARPS) {
     // ------------------------------------------------------------------------------ MMA issuer
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const Sa
     // ---------------------------------------------------------------------- gather / epilogues
     // thread t < 128 gathers row t (k 0..7 = [features | relative xyz | 0]); t >= 128 writes the
     // zero chunk k 8..15 of row t - 128 (the k-step is 16 wide)
+    bd::pdl_wait();  // neighbour indices and centres come from the preceding kernels
     const int r = tid & 127;
     const bool gatherer = tid < 128;
     const uint32_t a_off = tc::sw128_off(r, gatherer ? 0 : 1);
@@ -539,9 +543,9 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
     const int tiles = bd::ceil_div(p.M, SA_BM);
     const int ctas = tiles < 2 * n_sm ? tiles : 2 * n_sm;
     if (parts == 2)
-      sa_mlp_resident_kernel<2><<<ctas, SA_THREADS, smem_r, bd::as_stream(stream)>>>(p);
+      BD_CUDA(bd::launch_pdl(sa_mlp_resident_kernel<2>, dim3(ctas), dim3(SA_THREADS), smem_r, bd::as_stream(stream), p), "bd_sa_mlp_tc");
     else
-      sa_mlp_resident_kernel<1><<<ctas, SA_THREADS, smem_r, bd::as_stream(stream)>>>(p);
+      BD_CUDA(bd::launch_pdl(sa_mlp_resident_kernel<1>, dim3(ctas), dim3(SA_THREADS), smem_r, bd::as_stream(stream), p), "bd_sa_mlp_tc");
     BD_CHECK_LAUNCH("bd_sa_mlp_tc");
     return BD_OK;
   }
@@ -560,9 +564,9 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
   }
   const dim3 grid(bd::ceil_div(p.M, SA_BM));
   if (parts == 2)
-    sa_mlp_tc_kernel<2><<<grid, SA_THREADS, smem, bd::as_stream(stream)>>>(p);
+    BD_CUDA(bd::launch_pdl(sa_mlp_tc_kernel<2>, grid, dim3(SA_THREADS), smem, bd::as_stream(stream), p), "bd_sa_mlp_tc");
   else
-    sa_mlp_tc_kernel<1><<<grid, SA_THREADS, smem, bd::as_stream(stream)>>>(p);
+    BD_CUDA(bd::launch_pdl(sa_mlp_tc_kernel<1>, grid, dim3(SA_THREADS), smem, bd::as_stream(stream), p), "bd_sa_mlp_tc");
   BD_CHECK_LAUNCH("bd_sa_mlp_tc");
   return BD_OK;
 }

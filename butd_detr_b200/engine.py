@@ -65,13 +65,15 @@ FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = 
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
 
-def tc_tiling(N, K, split=1, full_rows=False, wide=False):
+def tc_tiling(N, K, split=1, full_rows=False, wide=False, bn=None):
     """(BN, KC, n_chunks, n_sub) for bd_linear_tc / bd_linear_ln_tc on an (N, K) weight.
     BN <= 160 columns per accumulator (multiple of 16); a CTA computes n_sub of them (all of
     them when `full_rows`, so that the LayerNorm epilogue sees complete rows); K is consumed in
     chunks of 64 (one 128-byte-swizzle block), zero padded."""
     nt = -(-N // 160)
     BN = _round_up(-(-N // nt), 16)
+    if bn is not None:  # caller-chosen accumulator width (latency tiling for small M, see lin_tiling)
+        BN, nt = bn, -(-N // bn)
     # `wide`: two accumulators per CTA, so the A tile is staged once for 2 x BN columns (measured
     # 1.3x on 32768-row GEMMs); small-M calls keep one per CTA for more CTAs in flight
     n_sub = nt if full_rows else (min(nt, 2) if wide else 1)
@@ -79,13 +81,28 @@ def tc_tiling(N, K, split=1, full_rows=False, wide=False):
     return BN, TC_KC, n_chunks, n_sub
 
 
-def pack_weight_tc(W, split=1, full_rows=False, wide=False):
+def lin_tiling(M, N, n_sm=148):
+    """(wide, bn) for bd_linear_tc on an (M, N) output: one accumulator per CTA while the grid
+    fits one wave of the 148 SMs (more CTAs in flight: 13.1 vs 16.2 us at M = 8192, N = 288), two
+    accumulators per CTA (the A tile staged once for 2 x BN columns) beyond that (66 vs 87 us at
+    M = 32768, N = 576)."""
+    rows = -(-M // 128)
+    nt = -(-N // 160)
+    bn = _round_up(-(-N // nt), 16)
+    if rows * nt > n_sm:
+        return (N > 160), None           # more than a wave anyway: wide tiles, fewer A stagings
+    # (accumulators narrower than the default were measured too: no gain — a CTA's time is its
+    #  operand-load chain, not its MMA / write-out width)
+    return False, None
+
+
+def pack_weight_tc(W, split=1, full_rows=False, wide=False, bn=None):
     """(N, K) fp32 -> bf16 blocks in the tensor-core kernels' shared-memory layout (128-byte
     swizzle, K-major; csrc/tc_common.cuh): Wp[n_group][k_chunk][part][sub][BN rows][64 k] where
     the 16-byte chunk j of row r holds k-chunk (j ^ (r % 8)); zero padded; part = {hi} or, for
     split 3, {hi, lo} with lo = bf16(W - hi)."""
     N, K = W.shape
-    BN, KC, n_chunks, n_sub = tc_tiling(N, K, split, full_rows, wide)
+    BN, KC, n_chunks, n_sub = tc_tiling(N, K, split, full_rows, wide, bn)
     ng = -(-N // (BN * n_sub))
     Wp = W.new_zeros(ng * n_sub * BN, n_chunks * KC)
     Wp[:N, :K] = W
@@ -248,10 +265,10 @@ class ForwardEngine:
         tc_ok = ((N >= 16 or M >= 1024) and K % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and
                  (add is None or (add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0)))
         if self.precision != "fp32" and tc_ok:  # tensor cores (narrow heads padded to 16 columns when M is large); K = 3 / 6 inputs stay fp32
-            wide = M >= 4096 and N > 160
-            tkey = key + "#wide" if wide else key
+            wide, bn = lin_tiling(M, N)
+            tkey = f"{key}#{'wide' if wide else bn}"
             if tkey not in self._tc:
-                self._tc[tkey] = pack_weight_tc(W, self.split, wide=wide)
+                self._tc[tkey] = pack_weight_tc(W, self.split, wide=wide, bn=bn)
             Wp, (BN, KC, n_chunks, n_sub) = self._tc[tkey]
             _lib.call("bd_linear_tc", x.data_ptr(), x.stride(0), _lib.ptr(add), lda2, Wp.data_ptr(), _lib.ptr(b),
                       out.data_ptr(), out.stride(0), M, N, K, KC, n_chunks, BN, n_sub, int(relu), self.split)

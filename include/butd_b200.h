@@ -233,6 +233,11 @@ int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int
                     const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
                     int B, int H, int Lq, int Lk, int hd, float scale, int split, void *workspace,
                     bd_stream_t stream);
+/* Programmatic dependent launch of the tensor-core kernels (each starts its prologue and weight
+ * copies under the tail of its predecessor in the stream and waits for it before touching
+ * activations): 1 = on (default), 0 = plain stream order.  Process-wide. */
+int bd_set_pdl(int enabled);
+
 /* Kernel generation used by bd_attention_tc: 1 = warp-specialised (loader / MMA issuer / two
  * softmax warpgroups, probabilities kept in TMEM; default), 0 = first-generation kernel (kept for
  * A/B measurements).  Process-wide; not meant to be flipped while launches are in flight. */
