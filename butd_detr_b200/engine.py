@@ -61,6 +61,8 @@ def _plain(sd, name):
 ORDERED_FPS = False  # SA1 FPS over the cell-list order with per-thread pruning (bd_fps_ordered): bit-identical, but
 # measured no faster (1.6 % of threads / 13 % of warps sweep per round, yet one lone sweeping warp still takes ~1000
 # cycles per round, as long as the whole un-pruned sweep with 4 warps per scheduler); kept for the tests and DESIGN.md §4
+DECODER_SPLIT_MIN = 1 << 30  # scenes per half above which the decoder would run as two batch halves on two streams:
+# measured at 32 scenes: 2336 vs 2400 scenes/s — no gain (the kernels of one half already fill a wave), so it is off
 FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
@@ -245,6 +247,7 @@ class ForwardEngine:
         self.text_stream = torch.cuda.Stream(device=self.device)
         self.kv_stream = torch.cuda.Stream(device=self.device)
         self.head_stream = torch.cuda.Stream(device=self.device)
+        self.dec_stream = torch.cuda.Stream(device=self.device)
         self._live = []  # every buffer of the current forward: nothing is recycled while streams overlap
 
     # ---- thin wrappers over the C-ABI (2-D row-major views; last stride must be 1)
@@ -352,31 +355,29 @@ class ForwardEngine:
     def posembed(self, x, key):
         return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
 
-    def head(self, feats, base_xyz, key, ep, prefix, B, Q):
-        """ClsAgnosticPredictHead.forward (models/modules.py:135-180) on token-major (B*Q, E)."""
+    def head(self, feats, base_xyz, key, out):
+        """ClsAgnosticPredictHead.forward (models/modules.py:135-180) on token-major rows (n, E).
+        `out`: dict of row views {center (n,3), size (n,3), sem (n,C)} of the full-batch outputs.
+        Class scores run on head_stream: nothing downstream on the calling stream needs them."""
         E = self.d_model
-        stem = self.lin(feats, key + ".stem", relu=True)  # (BQ, 3E)
-        outs = {}
-        main = torch.cuda.current_stream()
-        self.head_stream.wait_event(main.record_event())
-        with torch.cuda.stream(self.head_stream):  # class scores: not needed by the next decoder layer
+        stem = self.lin(feats, key + ".stem", relu=True)  # (n, 3E)
+        cur = torch.cuda.current_stream()
+        self.head_stream.wait_event(cur.record_event())
+        with torch.cuda.stream(self.head_stream):
             h = self.lin(stem[:, 2 * E:3 * E], f"{key}.sem.1", relu=True)
-            outs["sem"] = self.lin(h, f"{key}.sem.2")
-        for i, short in enumerate(("center", "size")):
-            h = self.lin(stem[:, i * E:(i + 1) * E], f"{key}.{short}.1", relu=True)
-            outs[short] = self.lin(h, f"{key}.{short}.2")
-        center = self._empty(B * Q, 3)
-        _lib.call("bd_add_rows", base_xyz.data_ptr(), 3, outs["center"].data_ptr(), 3, center.data_ptr(), 3, B * Q, 3)
-        ep[prefix + "base_xyz"] = base_xyz.view(B, Q, 3)
-        ep[prefix + "center"] = center.view(B, Q, 3)
-        ep[prefix + "pred_size"] = outs["size"].view(B, Q, 3)
-        ep[prefix + "sem_cls_scores"] = outs["sem"].view(B, Q, -1)
-        return center, outs["size"]
+            self.lin(h, f"{key}.sem.2", out=out["sem"])
+        h = self.lin(stem[:, :E], f"{key}.center.1", relu=True)
+        delta = self.lin(h, f"{key}.center.2")
+        h = self.lin(stem[:, E:2 * E], f"{key}.size.1", relu=True)
+        self.lin(h, f"{key}.size.2", out=out["size"])
+        n = feats.shape[0]
+        _lib.call("bd_add_rows", base_xyz.data_ptr(), 3, delta.data_ptr(), 3, out["center"].data_ptr(), 3, n, 3)
+        return out["center"], out["size"]
 
-    def contrastive(self, x, side, B, L):
+    def contrastive(self, x, side, B, L, out=None):
         h = self.lin(x, f"contrastive.{side}.0", relu=True)
         h = self.lin(h, f"contrastive.{side}.1", relu=True)
-        h = self.lin(h, f"contrastive.{side}.2")
+        h = self.lin(h, f"contrastive.{side}.2", out=out)
         _lib.call("bd_l2_normalize_rows", h.data_ptr(), h.data_ptr(), h.shape[0], h.shape[1])
         return h.view(B, L, -1)
 
@@ -692,39 +693,83 @@ class ForwardEngine:
             ep["query_points_feature"] = cluster_feat.view(B, Q, E).transpose(1, 2)
             ep["query_points_sample_inds"] = sample_inds
             query = self.lin(cluster_feat, "decoder_query_proj")
-            if cfg["contrastive_align_loss"]:
-                ep["proposal_proj_queries"] = self.contrastive(query, "image", B, Q)
-            base_xyz, base_size = self.head(cluster_feat, cluster_xyz, "proposal_head", ep, "proposal_", B, Q)
-            # ---- decoder (models/bdetr.py:278-317, encoder_decoder_layers.py:340-406)
             nd = cfg["num_decoder_layers"]
             spe = cfg["self_position_embedding"]
             hs = self.head_stream
-            for i in range(nd):
-                prefix = "last_" if i == nd - 1 else f"{i}head_"
-                k = f"dec{i}"
-                kv_l, kv_d, kv_v, kv_ready = mem_kv[i]
-                if spe == "loc_learned":  # query_pos = cat(base_xyz, base_size)  (bdetr.py:287)
-                    qp_in = self._empty(B * Q, 6)
-                    _lib.call("bd_concat_rows", base_xyz.data_ptr(), 3, 3, base_size.data_ptr(), 3, 3,
-                              qp_in.data_ptr(), 6, B * Q)
-                elif spe == "xyz_learned":
-                    qp_in = base_xyz
-                else:
-                    qp_in = None
-                qpos = self.posembed(qp_in, k + ".posembed") if qp_in is not None else None
-                query = self.mha(k + ".self", query, qpos, query, qpos, B, Q, Q, None, True, query, k + ".norm1")
-                main.wait_event(kv_ready)
-                query = self.mha(k + ".l", query, qpos, text, None, B, Q, L, tmask_u8, False, query, k + ".norm_l", kv=kv_l)
-                if cfg["butd"]:
-                    query = self.mha(k + ".d", query, qpos, det, None, B, Q, D, dmask_u8, False, query, k + ".norm_d",
-                                     kv=kv_d)
-                query = self.mha(k + ".v", query, qpos, vis, None, B, Q, V, None, False, query, k + ".norm_v", kv=kv_v)
-                query = self.ffn(query, k + ".ffn", k + ".norm2")
+            n_cls = self.W["proposal_head.sem.2"][0].shape[0]
+            prefixes = ["proposal_"] + ["last_" if i == nd - 1 else f"{i}head_" for i in range(nd)]
+            outs = {}
+            for pf in prefixes:  # full-batch outputs; the decoder parts below fill their rows
+                outs[pf] = {"center": self._empty(B * Q, 3), "size": self._empty(B * Q, 3),
+                            "sem": self._empty(B * Q, n_cls)}
                 if cfg["contrastive_align_loss"]:
-                    hs.wait_event(main.record_event())
+                    outs[pf]["proj"] = self._empty(B * Q, self.W["contrastive.image.2"][0].shape[0])
+
+            def rows(t, b0, b1, per):
+                return None if t is None else t[b0 * per:b1 * per]
+
+            def decode(b0, b1):
+                """Proposal head + the decoder layers for scenes [b0, b1) on the current stream
+                (models/bdetr.py:261-317, encoder_decoder_layers.py:340-406)."""
+                cur = torch.cuda.current_stream()
+                nb = b1 - b0
+                q = rows(query, b0, b1, Q)
+                cxyz = rows(cluster_xyz, b0, b1, Q)
+                tm, dm = rows(tmask_u8, b0, b1, 1), rows(dmask_u8, b0, b1, 1)
+                o = {k2: rows(v2, b0, b1, Q) for k2, v2 in outs["proposal_"].items()}
+                if cfg["contrastive_align_loss"]:
+                    hs.wait_event(cur.record_event())
                     with torch.cuda.stream(hs):
-                        ep[prefix + "proj_queries"] = self.contrastive(query, "image", B, Q)
-                base_xyz, base_size = self.head(query, cluster_xyz, f"head{i}", ep, prefix, B, Q)
+                        self.contrastive(q, "image", nb, Q, out=o["proj"])
+                base_xyz, base_size = self.head(rows(cluster_feat, b0, b1, Q), cxyz, "proposal_head", o)
+                for i in range(nd):
+                    k = f"dec{i}"
+                    kv_l, kv_d, kv_v, kv_ready = mem_kv[i]
+                    if spe == "loc_learned":  # query_pos = cat(base_xyz, base_size)  (bdetr.py:287)
+                        qp_in = self._empty(nb * Q, 6)
+                        _lib.call("bd_concat_rows", base_xyz.data_ptr(), 3, 3, base_size.data_ptr(), 3, 3,
+                                  qp_in.data_ptr(), 6, nb * Q)
+                    elif spe == "xyz_learned":
+                        qp_in = base_xyz
+                    else:
+                        qp_in = None
+                    qpos = self.posembed(qp_in, k + ".posembed") if qp_in is not None else None
+                    q = self.mha(k + ".self", q, qpos, q, qpos, nb, Q, Q, None, True, q, k + ".norm1")
+                    cur.wait_event(kv_ready)
+                    q = self.mha(k + ".l", q, qpos, None, None, nb, Q, L, tm, False, q, k + ".norm_l",
+                                 kv=rows(kv_l, b0, b1, L))
+                    if cfg["butd"]:
+                        q = self.mha(k + ".d", q, qpos, None, None, nb, Q, D, dm, False, q, k + ".norm_d",
+                                     kv=rows(kv_d, b0, b1, D))
+                    q = self.mha(k + ".v", q, qpos, None, None, nb, Q, V, None, False, q, k + ".norm_v",
+                                 kv=rows(kv_v, b0, b1, V))
+                    q = self.ffn(q, k + ".ffn", k + ".norm2")
+                    o = {k2: rows(v2, b0, b1, Q) for k2, v2 in outs[prefixes[i + 1]].items()}
+                    if cfg["contrastive_align_loss"]:
+                        hs.wait_event(cur.record_event())
+                        with torch.cuda.stream(hs):
+                            self.contrastive(q, "image", nb, Q, out=o["proj"])
+                    base_xyz, base_size = self.head(q, cxyz, f"head{i}", o)
+
+            # The decoder's kernels are short (256 queries per scene) and latency-bound; two halves
+            # of the batch on two streams overlap each other's dependent chains.
+            halves = [(0, B)] if B < 2 * DECODER_SPLIT_MIN else [(0, B // 2), (B // 2, B)]
+            ds = self.dec_stream
+            if len(halves) == 2:
+                ds.wait_event(main.record_event())
+                with torch.cuda.stream(ds):
+                    decode(*halves[1])
+            decode(*halves[0])
+            if len(halves) == 2:
+                main.wait_stream(ds)
             main.wait_stream(kvs)
             main.wait_stream(hs)
+            for i, pf in enumerate(prefixes):
+                o = outs[pf]
+                ep[pf + "base_xyz"] = cluster_xyz.view(B, Q, 3)  # every head is called with base_xyz = cluster_xyz
+                ep[pf + "center"] = o["center"].view(B, Q, 3)
+                ep[pf + "pred_size"] = o["size"].view(B, Q, 3)
+                ep[pf + "sem_cls_scores"] = o["sem"].view(B, Q, -1)
+                if cfg["contrastive_align_loss"]:
+                    ep[pf + "proj_queries"] = o["proj"].view(B, Q, -1)
         return ep
