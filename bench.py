@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="scenes per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="scenes per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of CUDA-graph replay")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
