@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
       const float v[8] = {a[it][0].x * mul, a[it][0].y * mul, a[it][0].z * mul, a[it][0].w * mul,
                           a[it][1].x * mul, a[it][1].y * mul, a[it][1].z * mul, a[it][1].w * mul};
       uint4 hi, lo;
-      tc::split_bf16x8(v, hi, lo);
+      tc::cvt8(PARTS, v, hi, lo);
       if (rr[it] < 0) continue;
       const uint32_t off = tc::sw128_off(rr[it], cc[it]);
       *reinterpret_cast<uint4 *>(dst + off) = hi;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
         v[i] = (d < AT_HD && key < p.Lk) ? __ldg(src + static_cast<long long>(key) * p.ldv + d) : (d == AT_HD ? 1.f : 0.f);
       }
       uint4 hi, lo;
-      tc::split_bf16x8(v, hi, lo);
+      tc::cvt8(PARTS, v, hi, lo);
       const uint32_t off = (kc >> 3) * V_BLK + tc::sw128_off(d, kc & 7);
       *reinterpret_cast<uint4 *>(dst + off) = hi;
       if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + V_PART + off) = lo;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(AT_THREADS, STAGES == 1 ? 2 : 1) attention_tc_
 #pragma unroll
   for (int i = 0; i < AT_HD; ++i) o_acc[i] = 0.f;
   uint32_t phase = 0;
-  const uint32_t idesc_s = tc::idesc_bf16(AT_BM, AT_BK), idesc_o = tc::idesc_bf16(AT_BM, AT_NV);
+  const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, AT_BK), idesc_o = tc::idesc_ab(PARTS, AT_BM, AT_NV);
   const int n_tiles = p.nk;
 
   for (int j = 0; j < n_tiles; ++j) {
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(AT_THREADS, STAGES == 1 ? 2 : 1) attention_tc_
         const float v8[8] = {pv[c2 * 8 + 0], pv[c2 * 8 + 1], pv[c2 * 8 + 2], pv[c2 * 8 + 3],
                              pv[c2 * 8 + 4], pv[c2 * 8 + 5], pv[c2 * 8 + 6], pv[c2 * 8 + 7]};
         uint4 hi, lo;
-        tc::split_bf16x8(v8, hi, lo);
+        tc::cvt8(PARTS, v8, hi, lo);
         const int kc = g * 2 + c2;  // 16-byte chunk of keys
         const uint32_t off = (kc >> 3) * P_BLK + tc::sw128_off(tid, kc & 7);
         *reinterpret_cast<uint4 *>(sP + off) = hi;
@@ -371,7 +371,7 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long ne
       if (PARTS == 2) {
         tc::split_bf16x2(p0, p1, o[i >> 1], o[16 + (i >> 1)]);
       } else {
-        o[i >> 1] = tc::pack_bf16x2(p0, p1);
+        o[i >> 1] = tc::pack_f16x2(p0, p1);
       }
     }
     if (PARTS == 2) {
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
     __syncwarp();
   } else if (warp == 1) {
     // -------------------------------------------------------------------------- MMA issuer
-    const uint32_t idesc_s = tc::idesc_bf16(AT_BM, WS_BK), idesc_o = tc::idesc_bf16(AT_BM, AT_NV);
+    const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, WS_BK), idesc_o = tc::idesc_ab(PARTS, AT_BM, AT_NV);
     tc::mbar_wait(tc::smem_u32(&bar_q), 0);
     for (int j = 0; j <= nk; ++j) {  // iteration j: P.V of key tile j-1, then Q.K^T of key tile j
       for (int t = 0; t < nt; ++t) {
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
           }
         }
         uint4 hi, lo;
-        tc::split_bf16x8(v, hi, lo);
+        tc::cvt8(PARTS, v, hi, lo);
         unsigned char *dst = sQ + (rr >> 7) * Q_TILE + tc::sw128_off(rr & 127, ch);
         *reinterpret_cast<uint4 *>(dst) = hi;
         if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + QK_PART) = lo;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   tc::fence_after_sync();
   TC_STAMP(1);
   const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
-  const uint32_t idesc = tc::idesc_bf16(TC_BM, BN);
+  const uint32_t idesc = tc::idesc_ab(static_cast<int>(parts), TC_BM, BN);
   __shared__ float bias_s[512];
 
   // Per-thread staging plan, identical for every k-chunk.  A warp-item covers 8 rows x 4 chunks
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = ok ? v[i] : 0.f;
         uint4 hi, lo;
-        tc::split_bf16x8(v, hi, lo);
+        tc::cvt8(static_cast<int>(parts), v, hi, lo);
         *reinterpret_cast<uint4 *>(sA + s_off[it]) = hi;
         if (parts == 2) *reinterpret_cast<uint4 *>(sA + A_PART + s_off[it]) = lo;
       }

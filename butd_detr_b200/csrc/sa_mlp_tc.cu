@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpPar
     int t = 0;
     for (int l = 0; l < 3; ++l) {
       const SaLayer &L = p.L[l];
-      const uint32_t idesc = tc::idesc_bf16(SA_BM, L.BN);
+      const uint32_t idesc = tc::idesc_ab(PARTS, SA_BM, L.BN);
       const uint32_t w_blk = static_cast<uint32_t>(L.BN) * 128u;
       const int k_total = l == 0 ? p.K1 : p.L[l - 1].N;  // valid K of this layer
       if (l > 0) {  // hidden activations of the previous layer are in shared memory (and TMEM was drained)
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpPar
         if (k_off[it] >= kend) continue;
         const float v[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w, ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
         uint4 hi, lo;
-        tc::split_bf16x8(v, hi, lo);
+        tc::cvt8(PARTS, v, hi, lo);
         *reinterpret_cast<uint4 *>(sA + s_off[it]) = hi;
         if (PARTS == 2) *reinterpret_cast<uint4 *>(sA + A_PART + s_off[it]) = lo;
       }
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpPar
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(acc[u][h8 * 8 + j]) + bias_s[l][k0 + h8 * 8 + j], 0.f);
               uint4 hi, lo;
-              tc::split_bf16x8(v, hi, lo);
+              tc::cvt8(PARTS, v, hi, lo);
               const int k = k0 + h8 * 8;
               const uint32_t off = static_cast<uint32_t>(k / KC) * A_PART + tc::sw128_off(r, (k % KC) / 8);
               *reinterpret_cast<uint4 *>(sX + off) = hi;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const Sa
       tc::bulk_g2s(tc::smem_u32(sW2), p.L[2].Wp, w2_bytes, bar);
     }
     tc::mbar_wait(tc::smem_u32(&bar_w), 0);
-    const uint32_t idesc64 = tc::idesc_bf16(SA_BM, 64), idesc2 = tc::idesc_bf16(SA_BM, N2);
+    const uint32_t idesc64 = tc::idesc_ab(PARTS, SA_BM, 64), idesc2 = tc::idesc_ab(PARTS, SA_BM, N2);
     const uint32_t a0 = tc::smem_u32(sX);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const Sa
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       {  // layer-1 operand (the previous tile's layer-3 MMAs, which read this region, were waited for)
         uint4 hi, lo;
-        tc::split_bf16x8(v, hi, lo);
+        tc::cvt8(PARTS, v, hi, lo);
         *reinterpret_cast<uint4 *>(sX + a_off) = hi;
         if (PARTS == 2) *reinterpret_cast<uint4 *>(sX + A_PART + a_off) = lo;
         tc::fence_before_sync();  // this thread's TMEM reads of the previous tile are complete
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const Sa
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(acc[u][h8 * 8 + j]) + bias_s[l][k + j], 0.f);
             uint4 hi, lo;
-            tc::split_bf16x8(o, hi, lo);
+            tc::cvt8(PARTS, o, hi, lo);
             const uint32_t off = tc::sw128_off(row, k / 8);
             *reinterpret_cast<uint4 *>(sX + off) = hi;
             if (PARTS == 2) *reinterpret_cast<uint4 *>(sX + A_PART + off) = lo;

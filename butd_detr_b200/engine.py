@@ -108,8 +108,11 @@ def pack_weight_tc(W, split=1, full_rows=False, wide=False, bn=None):
     ng = -(-N // (BN * n_sub))
     Wp = W.new_zeros(ng * n_sub * BN, n_chunks * KC)
     Wp[:N, :K] = W
-    hi = Wp.to(torch.bfloat16)
-    parts = [hi] if split == 1 else [hi, (Wp - hi.float()).to(torch.bfloat16)]
+    if split == 1:  # single-pass mode: fp16 operands (csrc/tc_common.cuh); both dtypes are 2 bytes
+        parts = [Wp.to(torch.float16).view(torch.bfloat16)]
+    else:
+        hi = Wp.to(torch.bfloat16)
+        parts = [hi, (Wp - hi.float()).to(torch.bfloat16)]
     P = torch.stack(parts, 0).view(len(parts), ng, n_sub, BN, n_chunks, 8, 8)  # (..., row, kc, chunk, elem)
     r = torch.arange(BN, device=W.device) % 8
     src_chunk = torch.arange(8, device=W.device)[None, :] ^ r[:, None]         # (BN, 8): logical chunk at slot j
@@ -232,8 +235,9 @@ class ForwardEngine:
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items() if not k.startswith("text_encoder.")}
         self.W = PackedWeights(sd, self.cfg)
         self.precision = cfg.get("precision", "fp32")
-        if self.precision not in ("fp32", "bf16", "bf16x3"):
-            raise ValueError("precision must be 'fp32' (SIMT), 'bf16' or 'bf16x3' (tcgen05)")
+        if self.precision not in ("fp32", "fp16", "bf16x3"):
+            raise ValueError("precision must be 'fp32' (SIMT), 'fp16' (tcgen05, fp16 operands, one MMA per product) "
+                             "or 'bf16x3' (tcgen05, bf16 hi/lo split operands, three MMAs per product)")
         self.split = 3 if self.precision == "bf16x3" else 1
         self._tc = {}  # key -> (packed bf16 weight, (BN, KC, n_chunks)), built on first use
         self.d_model = cfg["d_model"]

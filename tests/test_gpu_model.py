@@ -100,16 +100,17 @@ def test_batch_rows_are_independent(cuda_lib):
     assert torch.equal(full["sa1_inds"][1:2], one["sa1_inds"])
 
 
-@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("fp16", 1e-2)])
 @pytest.mark.parametrize("name", ["c1", "c2"])
 def test_tensor_core_forward_matches_reference_golden(name, precision, tol, cuda_lib, golden_dir):
     """Tensor-core modes (BASELINE.json configs[1]).  'bf16x3' (bf16 hi/lo split operands, three
     tcgen05 MMAs per product, fp32 accumulation) is the shipped mode and must meet even the fp32
-    gate (1e-3, hence the 1e-2 bf16 gate with margin).  Plain single-pass 'bf16' operands land
-    at 1-2e-2 after ~30 stacked post-LN GEMM layers — just outside the 1e-2 gate — and is kept
-    only as a measured comparison point (sanity bound 5e-2).  Query selection is teacher-forced with the reference's indices (SURVEY.md §7 hard
-    part 3: 1e-2 perturbations reorder the near-tied top-k scores, which permutes per-query
-    outputs without changing their values); the selection agreement is reported."""
+    gate (1e-3).  'fp16' (fp16 operands, one MMA per product) must meet the reduced-precision gate
+    (1e-2); plain bf16 operands did not (1.2-2.2e-2 after ~30 stacked post-LN GEMM layers), which
+    is why the single-pass mode uses fp16's 11 significant bits.  Query selection is
+    teacher-forced with the reference's indices (SURVEY.md §7 hard part 3: 1e-2 perturbations
+    reorder the near-tied top-k scores, which permutes per-query outputs without changing their
+    values); the selection agreement is reported."""
     gold = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
     model, inputs = build(name, cuda_lib, precision=precision)
     dev_in = {k: v.cuda() for k, v in inputs.items()}

@@ -1,5 +1,5 @@
-"""GPU numerics of the tcgen05 (bf16 operands, fp32 accumulate) kernels vs PyTorch on the same
-bf16-rounded operands.  Tolerance: accumulation-order noise only (1e-4 relative)."""
+"""GPU numerics of the tcgen05 kernels (split 1: fp16 operands, split 3: bf16 hi/lo operands; fp32
+accumulate) vs PyTorch on the same rounded operands.  Tolerance: accumulation-order noise only (1e-4 relative)."""
 import math
 
 import pytest
@@ -33,8 +33,8 @@ def test_linear_tc(cuda_lib, M, N, K, relu, add, split):
                   M, N, K, KC, nch, BN, nsub, int(relu), split)
     torch.cuda.synchronize()
     a = A + A2 if add else A
-    if split == 1:  # plain bf16 operands: compare with the same rounding applied
-        want = F.linear(a.bfloat16().double(), W.bfloat16().double(), b.double())
+    if split == 1:  # fp16 operands: compare with the same rounding applied
+        want = F.linear(a.half().double(), W.half().double(), b.double())
         tol = 1e-4
     else:           # bf16x3: fp32-grade
         want = F.linear(a.double(), W.double(), b.double())
@@ -53,7 +53,7 @@ def test_linear_tc_strided(cuda_lib):
     x = big[:, 288:576]
     cuda_lib.call("bd_linear_tc", x.data_ptr(), 864, None, 0, Wp.data_ptr(), None, out[:, 128:].data_ptr(), 288,
                   300, 160, 288, KC, nch, BN, nsub, 0, 1)
-    want = (x.bfloat16().double() @ W.bfloat16().double().t()).float()
+    want = (x.half().double() @ W.half().double().t()).float()
     torch.testing.assert_close(out[:, 128:], want, rtol=1e-4, atol=1e-4)
     assert float(out[:, :128].abs().max()) == 0.0
 
@@ -77,7 +77,7 @@ def test_linear_ln_tc(cuda_lib, M, N, K, add, split):
                   gam.data_ptr(), bet.data_ptr(), 1e-5, Y.data_ptr(), N, M, N, K, KC, nch, BN, nsub, split)
     a = A + A2 if add else A
     if split == 1:
-        lin = F.linear(a.bfloat16().double(), W.bfloat16().double(), b.double())
+        lin = F.linear(a.half().double(), W.half().double(), b.double())
     else:
         lin = F.linear(a.double(), W.double(), b.double())
     want = F.layer_norm(R.double() + lin, (N,), gam.double(), bet.double(), 1e-5).float()
@@ -115,7 +115,7 @@ def test_attention_tc(cuda_lib, B, Lq, Lk, masked, split, impl):
         s = s.masked_fill(mask[:, None, None, :], float("-inf"))
     want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
     cuda_lib.load().bd_attention_tc_select(1)
-    tol = 2e-2 if split == 1 else 1e-4
+    tol = 5e-3 if split == 1 else 1e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)
 
 
@@ -147,11 +147,11 @@ def test_sa_mlp_tc(cuda_lib, B, n, m, ns, C, widths, split):
     x = torch.cat([gx, feats[bi, idx.long()]], -1).double()  # reference order [xyz | feats]
     for i in range(3):
         if split == 1:
-            x = x.float().bfloat16().double()
-            w = Ws[i].bfloat16().double()
+            x = x.float().half().double()
+            w = Ws[i].half().double()
         else:
             w = Ws[i].double()
         x = torch.relu(x @ w.T + bs[i].double())
     want = x.max(2).values.reshape(B * m, -1).float()
-    tol = 3e-2 if split == 1 else 2e-4
+    tol = 1e-2 if split == 1 else 2e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from test_gpu_model import build, CFG
 name = sys.argv[1] if len(sys.argv) > 1 else "c1"
 gold = np.load(f"tests/golden/model_{name}.npz")
-model, inputs = build(name, None, precision=sys.argv[2] if len(sys.argv) > 2 else "bf16")
+model, inputs = build(name, None, precision=sys.argv[2] if len(sys.argv) > 2 else "fp16")
 ep = model({k: v.cuda() for k, v in inputs.items()}, overrides={"sample_inds": torch.from_numpy(gold["query_points_sample_inds"])})
 for k in gold.files:
     if k.startswith("__") or gold[k].dtype.kind in "iub":
