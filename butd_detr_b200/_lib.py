@@ -22,6 +22,7 @@ _SIGNATURES = {
     "bd_fps": [_P, _I, _I, _I, _I, _P, _P, _P],
     "bd_fps_set_cluster": [_I],
     "bd_set_pdl": [_I],
+    "bd_linear_tc_set_occupancy": [_I],
     "bd_fps_ordered": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "bd_grid_build": [_P, _I, _I, _I, _F, _P, _P],
     "bd_ball_query_grid_query": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P],

@@ -18,19 +18,23 @@
 //        or, for the fused variant (CTA owns complete rows, N <= 320), + residual -> LayerNorm.
 //
 // Replaces the cuBLAS / cuDNN-1x1-conv + BN + ReLU / LayerNorm call sites of the reference.
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "tc_common.cuh"
 
 namespace {
 
+int g_tc_two_per_sm = 1;  // bd_linear_tc_set_occupancy()
 constexpr int TC_BM = 128;
 constexpr int TC_WARPS = 8;                       // producer / epilogue warps
-constexpr int TC_THREADS = (TC_WARPS + 1) * 32;  // + one MMA-issuing warp
+constexpr int TC_THREADS = (TC_WARPS + 2) * 32;  // + one MMA-issuing warp + one loader warp
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ITEMS = 4;  // staged items (8 consecutive k of one row) per thread and k-chunk
 constexpr int KC = tc::KB;   // k-chunk = one 64-element swizzle block
 constexpr uint32_t A_PART = TC_BM * KC * 2;  // 16 KB
 
 struct LinearTcParams {
+  CUtensorMap tmA;  // plain-A variants: A as a 2-D tensor (K inner, M rows), box = 64 k x 128 rows, no swizzle
   const float *A, *A2, *bias, *R, *gamma, *beta;
   const __nv_bfloat16 *Wp;
   float *Y;
@@ -59,14 +63,14 @@ struct LinearTcParams {
 // MODE: 0 = A, 1 = A + A2, 2 = gathered rows (QueryAndGroup).  EPI: 0 = bias/ReLU, 1 = residual + LayerNorm,
 // 2 = bias/ReLU + max-pool over groups of rows.
 template <int EPI, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) linear_tc_kernel(const LinearTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) linear_tc_kernel(const __grid_constant__ LinearTcParams p) {
   constexpr bool LN_EPI = EPI == 1;
   constexpr bool HAS_A2 = MODE == 1;
   constexpr bool GATHER = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // swizzle-128B tiles need 1024-byte aligned bases (in the shared address space)
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) unsigned long long bar_w[TC_MAX_STAGES], bar_a[TC_MAX_STAGES], bar_mma[TC_MAX_STAGES], bar_done;
+  __shared__ __align__(8) unsigned long long bar_w[TC_MAX_STAGES], bar_a[TC_MAX_STAGES], bar_mma[TC_MAX_STAGES], bar_raw[TC_MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -78,7 +82,8 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   const int BN = p.BN, n_sub = p.n_sub;
   const uint32_t parts = p.split == 3 ? 2u : 1u;
   const uint32_t w_blk = static_cast<uint32_t>(BN) * KC * 2;  // multiple of 1024 (BN % 8 == 0)
-  const uint32_t a_bytes = A_PART * parts, w_bytes = w_blk * parts * n_sub;
+  constexpr bool TMA_A = MODE == 0;  // plain A: raw fp32 rows arrive by bulk copy and are converted in place
+  const uint32_t a_bytes = TMA_A ? 2 * A_PART : A_PART * parts, w_bytes = w_blk * parts * n_sub;
   const uint32_t stage_bytes = a_bytes + w_bytes;
   const uint32_t ncols = tc::tmem_cols_pow2(n_sub * BN);
 
@@ -88,6 +93,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
       tc::mbar_init(tc::smem_u32(&bar_w[i]), 1);
       tc::mbar_init(tc::smem_u32(&bar_a[i]), TC_WARPS);
       tc::mbar_init(tc::smem_u32(&bar_mma[i]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_raw[i]), 1);
     }
     tc::mbar_init(tc::smem_u32(&bar_done), 1);
     tc::fence_mbar_init();
@@ -178,9 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   };
 
   if (warp == TC_WARPS) {
-    // ------------------------------------ MMA issuer (also requests the first weight blocks)
-    if (lane == 0)
-      for (int c = 0; c < S && c < p.n_chunks; ++c) issue_w(c);
+    // ------------------------------------------------------------------------------ MMA issuer
     for (int c = 0; c < p.n_chunks; ++c) {
       const int st = c % S;
       const uint32_t par = (c / S) & 1;
@@ -214,18 +218,87 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
 
       TC_STAMP_T(12 + 3 * c, TC_WARPS * 32);
     }
+  } else if (warp == TC_WARPS + 1) {
+    // ---------------------------------------------------------------------------------- loader
+    // weight block of every chunk, and (plain-A variants) the chunk's raw fp32 activation rows:
+    // one bulk copy of <= 256 bytes per row straight into the stage's A region [128 rows x 256 B].
+    // The TMA path ingests ~2x what the LSU path (global loads into registers) does per SM.
+    if (lane == 0)
+      for (int c = 0; c < S && c < p.n_chunks; ++c) issue_w(c);
+    if (TMA_A) {
+      bd::pdl_wait();  // activations come from the preceding kernels
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const int st = c % S;
+        if (c >= S) tc::mbar_wait(tc::smem_u32(&bar_mma[st]), ((c / S) - 1) & 1);
+        if (lane == 0) {
+          if (c >= S) issue_w(c);
+          // one tensor copy per chunk: box (64 k x 128 rows) at (c * 64, row0); rows >= M and k >= K
+          // are zero-filled by the TMA unit and still count towards the full 32 KB
+          const uint32_t bar = tc::smem_u32(&bar_raw[st]);
+          tc::mbar_arrive_expect_tx(bar, 2 * A_PART);
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                  tc::smem_u32(smem + st * stage_bytes)),
+              "l"(reinterpret_cast<uint64_t>(&p.tmA)), "r"(c * KC), "r"(row0), "r"(bar)
+              : "memory");
+        }
+        __syncwarp();
+      }
+    } else {
+      for (int c = S; c < p.n_chunks; ++c) {  // refills (the producers only wait for the stage)
+        tc::mbar_wait(tc::smem_u32(&bar_mma[c % S]), ((c / S) - 1) & 1);
+        if (lane == 0) issue_w(c);
+      }
+    }
   } else {
     // ------------------------------------------------------------------------------- producers
     bd::pdl_wait();  // activations (A, A2, gather sources, residual) come from the preceding kernels
-    issue_loads(0, ra0, rb0);
-    if (p.n_chunks > 1) issue_loads(1, ra1, rb1);
+    if (!TMA_A) {
+      issue_loads(0, ra0, rb0);
+      if (p.n_chunks > 1) issue_loads(1, ra1, rb1);
+    }
     TC_STAMP(2);
+    // plain-A variant: read the raw chunk (lane = 16-byte piece of a row: 2 rows per warp
+    // instruction, conflict-free), barrier among the producers, write the converted operand over it
+    auto step_tma = [&](int c) {
+      const int st = c % S;
+      unsigned char *sA = smem + st * stage_bytes;
+      tc::mbar_wait(tc::smem_u32(&bar_raw[st]), (c / S) & 1);
+      float4 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 16 + 2 * i + (lane >> 4);
+        raw[i] = *reinterpret_cast<const float4 *>(sA + r * (KC * 4) + (lane & 15) * 16);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // every raw value is in registers
+      const int piece = lane & 15;
+      const bool k_ok = c * KC + piece * 4 < p.K;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 16 + 2 * i + (lane >> 4);
+        const bool ok = k_ok && row0 + r < p.M;
+        const float v0 = ok ? raw[i].x : 0.f, v1 = ok ? raw[i].y : 0.f, v2 = ok ? raw[i].z : 0.f, v3 = ok ? raw[i].w : 0.f;
+        const uint32_t off = tc::sw128_off(r, piece >> 1) + (piece & 1) * 8;
+        if (parts == 2) {
+          uint32_t h0, l0, h1, l1;
+          tc::split_bf16x2(v0, v1, h0, l0);
+          tc::split_bf16x2(v2, v3, h1, l1);
+          *reinterpret_cast<uint2 *>(sA + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2 *>(sA + A_PART + off) = make_uint2(l0, l1);
+        } else {
+          *reinterpret_cast<uint2 *>(sA + off) = make_uint2(tc::pack_f16x2(v0, v1), tc::pack_f16x2(v2, v3));
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_a[st]));
+      TC_STAMP(4 + c);
+    };
     auto step = [&](int c, float4 (&ra)[TC_ITEMS][2], float4 (&rb)[TC_ITEMS][2]) {
       const int st = c % S;
       unsigned char *sA = smem + st * stage_bytes;
       if (c >= S) {  // the stage's previous tenant, chunk c - S, must have been consumed
         tc::mbar_wait(tc::smem_u32(&bar_mma[st]), ((c / S) - 1) & 1);
-        if (tid == 0) issue_w(c);  // refills come from a producer: MMA issue blocks the issuing warp
         TC_STAMP(30 + c);
       }
 #pragma unroll
@@ -249,9 +322,13 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_a[st]));
       TC_STAMP(4 + c);
     };
-    for (int c = 0; c < p.n_chunks; c += 2) {
-      step(c, ra0, rb0);
-      if (c + 1 < p.n_chunks) step(c + 1, ra1, rb1);
+    if (TMA_A) {
+      for (int c = 0; c < p.n_chunks; ++c) step_tma(c);
+    } else {
+      for (int c = 0; c < p.n_chunks; c += 2) {
+        step(c, ra0, rb0);
+        if (c + 1 < p.n_chunks) step(c + 1, ra1, rb1);
+      }
     }
     // bias -> shared memory while the last MMAs run
     for (int i = tid; i < n_sub * BN; i += TC_WARPS * 32) {
@@ -418,15 +495,55 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
 int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
+  if (!p.A2 && !p.g_idx) {  // plain-A variants read A through the TMA unit
+    EncodeTiledFn enc = encode_tiled();
+    BD_REQUIRE(enc != nullptr, "bd_linear_tc: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.K), static_cast<cuuint64_t>(p.M)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.lda) * sizeof(float)};
+    const cuuint32_t box[2] = {KC, TC_BM}, estr[2] = {1, 1};
+    const CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.A), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BD_REQUIRE(r == CUDA_SUCCESS, "bd_linear_tc: cuTensorMapEncodeTiled failed (%d) for M=%d K=%d lda=%d", static_cast<int>(r),
+               p.M, p.K, p.lda);
+  }
   const int NC = p.n_sub * p.BN;
   const uint32_t parts = p.split == 3 ? 2 : 1;
-  const size_t stage = static_cast<size_t>(parts) * (TC_BM + NC) * KC * 2;
+  const bool tma_a = !p.A2 && !p.g_idx;  // MODE 0: the A region holds the raw fp32 chunk first (32 KB)
+  const size_t stage = (tma_a ? 2 * A_PART : parts * A_PART) + static_cast<size_t>(parts) * NC * KC * 2;
   int stages = static_cast<int>((217 * 1024) / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.n_chunks) stages = p.n_chunks;
   BD_REQUIRE(stages >= 1 && (stages >= 2 || p.n_chunks == 1),
              "bd_linear_tc: a pipeline stage needs %zu bytes of shared memory; two must fit 217 KB", stage);
+  // Two CTAs per SM when that is possible at all (accumulators <= 256 TMEM columns, kernel variant
+  // compiled for two, at least two stages in 109 KB) and the grid is more than one wave: a CTA's
+  // timeline is serial (operand latency -> main loop -> write-out), the second CTA fills its gaps.
+  const int n_row_tiles = bd::ceil_div(p.M, TC_BM), n_col_groups = bd::ceil_div(p.N, NC);
+  if (g_tc_two_per_sm && !ln && !p.A2 && !p.g_idx && tc::tmem_cols_pow2(NC) <= 256 &&
+      static_cast<long long>(n_row_tiles) * n_col_groups > bd::sm_count()) {
+    const int s2 = static_cast<int>((109 * 1024 - 1024) / stage);
+    const size_t tile2 = static_cast<size_t>(TC_BM) * (NC + 4) * 4;
+    if (s2 >= 2 && tile2 + 1024 <= 109 * 1024 && s2 < stages) stages = s2;
+  }
   p.n_stages = stages;
   const size_t pipe = stage * stages;
   const size_t tile = static_cast<size_t>(TC_BM) * (NC + 4) * 4;
@@ -476,6 +593,13 @@ int check_common(const float *A, const void *Wp, float *Y, int lda, int A2_ok, i
 long long *g_tc_dbg = nullptr;
 
 }  // namespace
+
+// 1 (default): plain linears whose accumulators fit 256 TMEM columns limit their pipeline to 109 KB
+// of shared memory so that two CTAs share an SM; 0: always the deepest pipeline, one CTA per SM.
+extern "C" int bd_linear_tc_set_occupancy(int two_per_sm) {
+  g_tc_two_per_sm = two_per_sm ? 1 : 0;
+  return BD_OK;
+}
 
 // Tuning aid: device buffer of >= 64 long longs receiving clock64() stamps of CTA (0,0); NULL disables.
 extern "C" int bd_linear_tc_set_debug(long long *buf) {

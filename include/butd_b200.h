@@ -195,6 +195,10 @@ int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, int C, const 
                  const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
                  const float *b2, int N2, float *Y, int ldy, int split, bd_stream_t stream);
 
+/* Occupancy policy of bd_linear_tc / bd_linear_pool_tc: 1 (default) = two CTAs per SM where the
+ * accumulators fit 256 TMEM columns and the grid exceeds one wave; 0 = one CTA per SM, deepest ring. */
+int bd_linear_tc_set_occupancy(int two_per_sm);
+
 /* Tuning aid: device buffer (>= 64 x int64) that receives clock64() stamps of the phases of CTA
  * (0,0) of every following bd_linear*_tc launch; NULL disables. */
 int bd_linear_tc_set_debug(long long *buf);
