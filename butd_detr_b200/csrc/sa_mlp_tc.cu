@@ -48,7 +48,7 @@ struct SaMlpParams {
 };
 
 template <int PARTS>
-__global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpParams p) {
+__global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kernel(const SaMlpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char *sX = smem;              // layer 1: A ring (2 stages); layers 2, 3: hidden activations
@@ -265,38 +265,46 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaMlpPar
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_h));
       } else {
-        // ---- last layer: +bias, ReLU -> shared tile -> max over the nsample rows of each centre.
-        //      The tile reuses the A / W regions: every MMA and weight copy has completed.
-        const int ldt = L.N + 4;
+        // ---- last layer: +bias, ReLU -> shared tile -> max over the nsample rows of each centre,
+        //      in column passes of at most 128 (tile = 128 x 132 floats: small enough for two CTAs
+        //      per SM in the single-part mode).  The tile reuses the A / W regions: every MMA and
+        //      weight copy has completed.
+        const int PW = min(L.N, 128);  // columns per pass
+        const int ldt = PW + 4;
         float *tile = reinterpret_cast<float *>(smem);
-        for (int g = g0; g < g1; g += 2) {
-          uint32_t acc[2][16];
-          tc::tmem_ld16(tbase + g * 16, acc[0]);
-          if (g + 1 < g1) tc::tmem_ld16(tbase + (g + 1) * 16, acc[1]);
-          tc::tmem_ld_wait();
+        const int pg = PW / 16 / 2;  // 16-column groups per warpgroup and pass
+        for (int c0 = 0; c0 < L.N; c0 += PW) {
+          for (int g = 0; g < pg; g += 2) {
+            const int col = (warp >> 2) * (PW / 2) + g * 16;  // column inside the pass
+            uint32_t acc[2][16];
+            tc::tmem_ld16(tbase + c0 + col, acc[0]);
+            if (g + 1 < pg) tc::tmem_ld16(tbase + c0 + col + 16, acc[1]);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (g + u >= g1) break;
-            float o[16];
+            for (int u = 0; u < 2; ++u) {
+              if (g + u >= pg) break;
+              float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = fmaxf(__uint_as_float(acc[u][j]) + bias_s[l][(g + u) * 16 + j], 0.f);
-            float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + (g + u) * 16);
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-            dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-            dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(__uint_as_float(acc[u][j]) + bias_s[l][c0 + col + u * 16 + j], 0.f);
+              float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + col + u * 16);
+              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+              dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+            }
           }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int groups = SA_BM / p.ns;
-        for (int e = tid; e < groups * L.N; e += SA_WARPS * 32) {
-          const int g = e / L.N, col = e - g * L.N;
-          const long long orow = static_cast<long long>(row0) / p.ns + g;
-          if (orow * p.ns >= p.M) continue;
-          const float *tt = tile + (g * p.ns) * ldt + col;
-          float mx = tt[0];
-          for (int q = 1; q < p.ns; ++q) mx = fmaxf(mx, tt[q * ldt]);
-          p.Y[orow * p.ldy + col] = mx;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int groups = SA_BM / p.ns;
+          for (int e = tid; e < groups * PW; e += SA_WARPS * 32) {
+            const int g = e / PW, col = e - g * PW;
+            const long long orow = static_cast<long long>(row0) / p.ns + g;
+            if (orow * p.ns >= p.M) continue;
+            const float *tt = tile + (g * p.ns) * ldt + col;
+            float mx = tt[0];
+            for (int q = 1; q < p.ns; ++q) mx = fmaxf(mx, tt[q * ldt]);
+            p.Y[orow * p.ldy + c0 + col] = mx;
+          }
+          if (c0 + PW < L.N) asm volatile("bar.sync 1, 256;" ::: "memory");  // tile free for the next pass
         }
       }
     }
@@ -553,7 +561,7 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
   const uint32_t hidden = static_cast<uint32_t>(parts) * (static_cast<uint32_t>(N0 > N1 ? N0 : N1) / KC) * A_PART;
   p.x_bytes = a_ring > hidden ? a_ring : hidden;
   const size_t pipe = static_cast<size_t>(p.x_bytes) + 2u * w_stage;
-  const size_t tile = static_cast<size_t>(SA_BM) * (N2 + 4) * 4;
+  const size_t tile = static_cast<size_t>(SA_BM) * ((N2 < 128 ? N2 : 128) + 4) * 4;  // pooled in passes of <= 128 columns
   const size_t smem = (pipe > tile ? pipe : tile) + 1024;
   BD_REQUIRE(smem <= 218 * 1024, "bd_sa_mlp_tc: needs %zu bytes of shared memory (> 218 KB)", smem);
   static thread_local bool configured = false;
