@@ -170,7 +170,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout at the first communicator: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
     model = BeaUTyDETR(text_encoder=None, cuda_graph=not args.no_graph, precision=args.precision)
     synth.fill_state_dict_(model.state_dict(), 0)
