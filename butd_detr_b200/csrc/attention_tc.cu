@@ -354,11 +354,16 @@ constexpr int WS_THREADS = 384, WS_BK = 128;
 // second softmax pass over one 128-key score row held in TMEM (see attention_ws_kernel)
 template <int PARTS, bool MASKED>
 __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long neg_m2, const uint32_t (&vw)[4], bool dead) {
+  // the load of chunk c + 1 is in flight while chunk c is exponentiated (distinct columns: the
+  // in-place store of chunk c cannot touch them)
+  uint32_t ab[2][32];
+  tc::tmem_ld32(tS, ab[0]);
+  tc::tmem_ld_wait();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t a[32], o[32];
-    tc::tmem_ld32(tS + c * 32, a);
-    tc::tmem_ld_wait();
+    uint32_t o[32];
+    uint32_t(&a)[32] = ab[c & 1];
+    if (c + 1 < 4) tc::tmem_ld32(tS + (c + 1) * 32, ab[(c + 1) & 1]);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       float x0 = __uint_as_float(a[i]), x1 = __uint_as_float(a[i + 1]);
@@ -382,6 +387,7 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long ne
       for (int i = 0; i < 16; ++i) o16[i] = o[i];
       tc::tmem_st16(tS + c * 32, o16);
     }
+    if (c + 1 < 4) tc::tmem_ld_wait();
   }
 }
 
