@@ -65,13 +65,15 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
                                : p.Kp + (static_cast<size_t>(b) * p.H + h) * p.nk * (PARTS * K_PART)) +
                          static_cast<size_t>(t) * (PARTS * part);
     src += h * AT_HD;
-    // 128 rows x 8 chunks = 1024 items, 4 per thread, loads batched
-    float4 a[4][2];
-    int rr[4], cc[4];
+    // 128 rows x 6 chunks (the three K = 16 steps read chunks 0..5; 36 dims -> chunks 0..4, chunk 5
+    // is zero) = 768 items, 3 per thread, chunk-fastest: the lanes of a warp read ~5 whole rows
+    // (144 contiguous bytes each) instead of 32 different ones; loads batched
+    float4 a[3][2];
+    int rr[3], cc[3];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 3; ++it) {
       const int e = tid + it * 256;
-      const int r = e & 127, ch = e >> 7;  // consecutive threads -> consecutive rows
+      const int r = e / 6, ch = e - r * 6;
       rr[it] = r < tile_rows ? r : -1, cc[it] = ch;
       a[it][0] = a[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < tile_rows && row0 + r < n_rows && ch * 8 < AT_HD) {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
       }
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 3; ++it) {
       const float v[8] = {a[it][0].x * mul, a[it][0].y * mul, a[it][0].z * mul, a[it][0].w * mul,
                           a[it][1].x * mul, a[it][1].y * mul, a[it][1].z * mul, a[it][1].w * mul};
       uint4 hi, lo;
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(AT_THREADS, STAGES == 1 ? 2 : 1) attention_tc_
       if (tc::elect_one()) {
         const uint32_t q = tc::smem_u32(sQ), k = tc::smem_u32(sKV + st * KV_STAGE);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < 3; ++s) {  // head_dim 36 -> 48: chunks 6, 7 of the tiles are not written
           const uint64_t dq = tc::smem_desc_sw128(q + s * 32), dk = tc::smem_desc_sw128(k + s * 32);
           tc::mma_bf16(tmem_s, dq, dk, idesc_s, s > 0 ? 1u : 0u);
           if (PARTS == 2) {
