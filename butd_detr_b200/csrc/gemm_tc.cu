@@ -34,7 +34,7 @@ constexpr int KC = tc::KB;   // k-chunk = one 64-element swizzle block
 constexpr uint32_t A_PART = TC_BM * KC * 2;  // 16 KB
 
 struct LinearTcParams {
-  CUtensorMap tmA;  // plain-A variants: A as a 2-D tensor (K inner, M rows), box = 64 k x 128 rows, no swizzle
+  CUtensorMap tmA, tmA2;  // A (and A2) as 2-D tensors (K inner, M rows), box = 64 k x 128 rows, no swizzle
   const float *A, *A2, *bias, *R, *gamma, *beta;
   const __nv_bfloat16 *Wp;
   float *Y;
@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   const int BN = p.BN, n_sub = p.n_sub;
   const uint32_t parts = p.split == 3 ? 2u : 1u;
   const uint32_t w_blk = static_cast<uint32_t>(BN) * KC * 2;  // multiple of 1024 (BN % 8 == 0)
-  constexpr bool TMA_A = MODE == 0;  // plain A: raw fp32 rows arrive by bulk copy and are converted in place
-  const uint32_t a_bytes = TMA_A ? 2 * A_PART : A_PART * parts, w_bytes = w_blk * parts * n_sub;
+  // A (and A2) arrive as raw fp32 chunks by tensor copy and are converted in place; the gathered
+  // variant stages through registers (LSU)
+  constexpr bool TMA_A = MODE == 0 || (MODE == 1 && EPI != 1);  // (LayerNorm + A2: full-row weights leave no room)
+  constexpr uint32_t RAW = 2 * A_PART;  // one raw fp32 chunk: 128 rows x 256 B
+  const uint32_t a_bytes = TMA_A ? (HAS_A2 ? 2 * RAW : RAW) : A_PART * parts, w_bytes = w_blk * parts * n_sub;
   const uint32_t stage_bytes = a_bytes + w_bytes;
   const uint32_t ncols = tc::tmem_cols_pow2(n_sub * BN);
 
@@ -235,12 +238,18 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
           // one tensor copy per chunk: box (64 k x 128 rows) at (c * 64, row0); rows >= M and k >= K
           // are zero-filled by the TMA unit and still count towards the full 32 KB
           const uint32_t bar = tc::smem_u32(&bar_raw[st]);
-          tc::mbar_arrive_expect_tx(bar, 2 * A_PART);
+          tc::mbar_arrive_expect_tx(bar, HAS_A2 ? 2 * RAW : RAW);
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                   tc::smem_u32(smem + st * stage_bytes)),
               "l"(reinterpret_cast<uint64_t>(&p.tmA)), "r"(c * KC), "r"(row0), "r"(bar)
               : "memory");
+          if (HAS_A2)
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                    tc::smem_u32(smem + st * stage_bytes + RAW)),
+                "l"(reinterpret_cast<uint64_t>(&p.tmA2)), "r"(c * KC), "r"(row0), "r"(bar)
+                : "memory");
         }
         __syncwarp();
       }
@@ -269,6 +278,10 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
       for (int i = 0; i < 8; ++i) {
         const int r = warp * 16 + 2 * i + (lane >> 4);
         raw[i] = *reinterpret_cast<const float4 *>(sA + r * (KC * 4) + (lane & 15) * 16);
+        if (HAS_A2) {  // + positional embedding (second raw chunk of the stage; never overwritten)
+          const float4 r2 = *reinterpret_cast<const float4 *>(sA + RAW + r * (KC * 4) + (lane & 15) * 16);
+          raw[i].x += r2.x, raw[i].y += r2.y, raw[i].z += r2.z, raw[i].w += r2.w;
+        }
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");  // every raw value is in registers
       const int piece = lane & 15;
@@ -513,22 +526,26 @@ EncodeTiledFn encode_tiled() {
 }
 
 int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
-  if (!p.A2 && !p.g_idx) {  // plain-A variants read A through the TMA unit
+  if (!p.g_idx && !(ln && p.A2)) {  // A (and A2) are read through the TMA unit
     EncodeTiledFn enc = encode_tiled();
     BD_REQUIRE(enc != nullptr, "bd_linear_tc: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.K), static_cast<cuuint64_t>(p.M)};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.lda) * sizeof(float)};
     const cuuint32_t box[2] = {KC, TC_BM}, estr[2] = {1, 1};
-    const CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.A), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    BD_REQUIRE(r == CUDA_SUCCESS, "bd_linear_tc: cuTensorMapEncodeTiled failed (%d) for M=%d K=%d lda=%d", static_cast<int>(r),
-               p.M, p.K, p.lda);
+    for (int which = 0; which < (p.A2 ? 2 : 1); ++which) {
+      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(which ? p.lda2 : p.lda) * sizeof(float)};
+      const CUresult r = enc(which ? &p.tmA2 : &p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                             const_cast<float *>(which ? p.A2 : p.A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      BD_REQUIRE(r == CUDA_SUCCESS, "bd_linear_tc: cuTensorMapEncodeTiled failed (%d) for M=%d K=%d ld=%d", static_cast<int>(r),
+                 p.M, p.K, which ? p.lda2 : p.lda);
+    }
   }
   const int NC = p.n_sub * p.BN;
   const uint32_t parts = p.split == 3 ? 2 : 1;
-  const bool tma_a = !p.A2 && !p.g_idx;  // MODE 0: the A region holds the raw fp32 chunk first (32 KB)
-  const size_t stage = (tma_a ? 2 * A_PART : parts * A_PART) + static_cast<size_t>(parts) * NC * KC * 2;
+  // the A region of a stage holds the raw fp32 chunk(s) first: 32 KB, 64 KB with A2; gather: the operand only
+  const bool lsu_a = p.g_idx || (ln && p.A2);
+  const size_t a_region = lsu_a ? parts * A_PART : (p.A2 ? 4 * A_PART : 2 * A_PART);
+  const size_t stage = a_region + static_cast<size_t>(parts) * NC * KC * 2;
   int stages = static_cast<int>((217 * 1024) / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.n_chunks) stages = p.n_chunks;

@@ -273,6 +273,8 @@ class ForwardEngine:
                  (add is None or (add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0)))
         if self.precision != "fp32" and tc_ok:  # tensor cores (narrow heads padded to 16 columns when M is large); K = 3 / 6 inputs stay fp32
             wide, bn = lin_tiling(M, N)
+            if add is not None and self.split == 3:
+                wide = False  # two raw fp32 chunks (x and pos) + hi/lo weights of a 288-wide tile: no room for 2 stages
             tkey = f"{key}#{'wide' if wide else bn}"
             if tkey not in self._tc:
                 self._tc[tkey] = pack_weight_tc(W, self.split, wide=wide, bn=bn)
