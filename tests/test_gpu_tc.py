@@ -155,3 +155,59 @@ def test_sa_mlp_tc(cuda_lib, B, n, m, ns, C, widths, split):
     want = x.max(2).values.reshape(B * m, -1).float()
     tol = 1e-2 if split == 1 else 2e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("M,N,K,add,wide", [(20000, 576, 288, False, True), (20000, 576, 288, True, False),
+                                            (33000, 288, 288, False, False), (19999, 256, 264, True, True)])
+def test_linear_tc_many_row_tiles(cuda_lib, M, N, K, add, wide, split):
+    """More row tiles than SMs (several waves, the two-CTAs-per-SM policy), a ragged last tile and a
+    K tail — the tensor copies of the activations zero-fill both; narrow and wide tilings."""
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(M + N + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    A2 = torch.randn(M, K, device="cuda", generator=g) if add else None
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, split, wide=wide and not (add and split == 3))
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    cuda_lib.call("bd_linear_tc", A.data_ptr(), K, cuda_lib.ptr(A2), K, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), N,
+                  M, N, K, KC, nch, BN, nsub, 1, split)
+    a = A + A2 if add else A
+    if split == 1:
+        want = F.linear(a.half().double(), W.half().double(), b.double())
+    else:
+        want = F.linear(a.double(), W.double(), b.double())
+    torch.testing.assert_close(Y, want.relu().float(), rtol=1e-4, atol=1e-4)
+
+
+def test_launch_policies_do_not_change_results(cuda_lib):
+    """Programmatic dependent launch on / off and one / two CTAs per SM: bit-identical outputs."""
+    from butd_detr_b200.engine import pack_weight_tc
+    lib = cuda_lib.load()
+    M, N, K = 40000, 288, 288
+    g = _g(7)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    outs = []
+    try:
+        for pdl, occ in ((1, 1), (0, 1), (1, 0), (0, 0)):
+            lib.bd_set_pdl(pdl)
+            lib.bd_linear_tc_set_occupancy(occ)
+            Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 3)
+            Y = torch.full((M, N), float("nan"), device="cuda")
+            H = torch.empty(M, N, device="cuda")
+            # a dependent chain: the second kernel reads what the first one wrote
+            cuda_lib.call("bd_linear_tc", A.data_ptr(), K, None, 0, Wp.data_ptr(), b.data_ptr(), H.data_ptr(), N, M, N, K,
+                          KC, nch, BN, nsub, 1, 3)
+            cuda_lib.call("bd_linear_tc", H.data_ptr(), N, None, 0, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), N, M, N, K,
+                          KC, nch, BN, nsub, 0, 3)
+            torch.cuda.synchronize()
+            outs.append(Y)
+    finally:
+        lib.bd_set_pdl(1)
+        lib.bd_linear_tc_set_occupancy(1)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert torch.isfinite(outs[0]).all()
