@@ -252,6 +252,7 @@ class ForwardEngine:
         self.kv_stream = torch.cuda.Stream(device=self.device)
         self.head_stream = torch.cuda.Stream(device=self.device)
         self.dec_stream = torch.cuda.Stream(device=self.device)
+        self.aux_stream = torch.cuda.Stream(device=self.device)  # short independent branches (V projection, size head)
         self._live = []  # every buffer of the current forward: nothing is recycled while streams overlap
 
     # ---- thin wrappers over the C-ABI (2-D row-major views; last stride must be 1)
@@ -341,10 +342,16 @@ class ForwardEngine:
         if self_attn and pos_q is None:  # q = k = v = x : one fused QKV GEMM
             qkv = self.lin(x_q, key + ".qkv")
             q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
-        elif self_attn:  # q = k = x + pos, v = x
+        elif self_attn:  # q = k = x + pos, v = x : the V projection runs beside the Q/K one
+            cur = torch.cuda.current_stream()
+            aux = self.aux_stream
+            aux.wait_event(cur.record_event())
+            with torch.cuda.stream(aux):
+                v = self.lin(x_q, key + ".v")
+                v_ready = aux.record_event()
             qk = self.lin(x_q, key + ".qk", add=pos_q)
             q, k = qk[:, :E], qk[:, E:]
-            v = self.lin(x_q, key + ".v")
+            cur.wait_event(v_ready)
         else:  # cross attention: k = v = memory (no positional term in this model)
             q = self.lin(x_q, key + ".q", add=pos_q)
             assert pos_k is None
@@ -372,12 +379,17 @@ class ForwardEngine:
         with torch.cuda.stream(self.head_stream):
             h = self.lin(stem[:, 2 * E:3 * E], f"{key}.sem.1", relu=True)
             self.lin(h, f"{key}.sem.2", out=out["sem"])
+        aux = self.aux_stream
+        aux.wait_event(cur.record_event())
+        with torch.cuda.stream(aux):  # the size branch beside the centre branch
+            h2 = self.lin(stem[:, E:2 * E], f"{key}.size.1", relu=True)
+            self.lin(h2, f"{key}.size.2", out=out["size"])
+            size_ready = aux.record_event()
         h = self.lin(stem[:, :E], f"{key}.center.1", relu=True)
         delta = self.lin(h, f"{key}.center.2")
-        h = self.lin(stem[:, E:2 * E], f"{key}.size.1", relu=True)
-        self.lin(h, f"{key}.size.2", out=out["size"])
         n = feats.shape[0]
         _lib.call("bd_add_rows", base_xyz.data_ptr(), 3, delta.data_ptr(), 3, out["center"].data_ptr(), 3, n, 3)
+        cur.wait_event(size_ready)
         return out["center"], out["size"]
 
     def contrastive(self, x, side, B, L, out=None):
