@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
 // warp REDUX on the (non-negative, hence integer-ordered) ReLU outputs — no shared tile.
 //   K1 <= 16 (one MMA k-step), N0 = N1 = 64, N2 in {64, 128}, nsample in {32, 64}.
 template <int PARTS>
-__global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const SaMlpParams p) {
+__global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_resident_kernel(const SaMlpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int N2 = p.L[2].N;
@@ -474,7 +474,11 @@ __global__ void __launch_bounds__(SA_THREADS, 2) sa_mlp_resident_kernel(const Sa
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float x = fmaxf(__uint_as_float(acc[j]) + bias_s[2][half * ncol + g * 16 + j], 0.f);
+#ifdef SA1_NO_POOL
+          const unsigned mx = __float_as_uint(x) & 0x7FFFFFFFu;
+#else
           const unsigned mx = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(x) & 0x7FFFFFFFu);
+#endif
           if (lane == j) mine = __uint_as_float(mx);
         }
         if (lane < 16) pool_s[warp & 3][half * ncol + g * 16 + lane] = mine;
@@ -549,7 +553,8 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
       configured_r = true;
     }
     const int tiles = bd::ceil_div(p.M, SA_BM);
-    const int ctas = tiles < 2 * n_sm ? tiles : 2 * n_sm;
+    const int per_sm = parts == 1 ? 3 : 2;  // 49 KB of shared memory per CTA in the single-part mode, 97 KB otherwise
+    const int ctas = tiles < per_sm * n_sm ? tiles : per_sm * n_sm;
     if (parts == 2)
       BD_CUDA(bd::launch_pdl(sa_mlp_resident_kernel<2>, dim3(ctas), dim3(SA_THREADS), smem_r, bd::as_stream(stream), p), "bd_sa_mlp_tc");
     else
