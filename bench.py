@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="scenes per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="scenes per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of CUDA-graph replay")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16x3"],
@@ -190,7 +190,7 @@ def main():
     # input pool larger than L2 (126 MB): rotate through distinct scenes so no step finds its
     # inputs cached; each rank gets its own scenes (data-parallel shard, no forward collective)
     bytes_per_scene = WORKLOAD["n_points"] * 6 * 4 + WORKLOAD["n_tokens"] * 768 * 4
-    n_pool = max(-(-160_000_000 // bytes_per_scene), B)
+    n_pool = max(-(-160_000_000 // bytes_per_scene), 2 * B)  # > L2, and at least two distinct batches
     n_pool = -(-n_pool // B) * B
     pool_cpu = make_pool(n_pool, 100000 * (rank + 1))
     pool_pinned = {k: v.pin_memory() for k, v in pool_cpu.items()}
