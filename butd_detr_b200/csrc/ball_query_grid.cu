@@ -16,6 +16,7 @@ namespace {
 constexpr int G_MAX = 1 << 16;   // cells per scene
 constexpr int Q_WARPS = 8;
 constexpr int Q_CAP = 768;       // hits kept per centre before falling back to the ordered scan
+constexpr int Q_SORT = 1024;     // Q_CAP rounded up to a power of two (bitonic sort padding)
 
 struct GridMeta {
   float minx, miny, minz, inv_cell;
@@ -148,20 +149,24 @@ __global__ void __launch_bounds__(1024) bq_scan_kernel(int *__restrict__ count, 
   for (int i = span + tid; i <= G_MAX; i += 1024) c[i] = total;
 }
 
-__global__ void bq_fill_kernel(int n, const int *__restrict__ cell_of, int *__restrict__ cursor,
-                               int *__restrict__ sorted) {
+// cell-ordered copies: the index (bd_grid_order) and (x, y, z, index) — the query then streams
+// 16-byte records of contiguous cells instead of chasing indices into the 24-byte point rows
+__global__ void bq_fill_kernel(const float *__restrict__ xyz, int ld, int n, const int *__restrict__ cell_of,
+                               int *__restrict__ cursor, int *__restrict__ sorted, float4 *__restrict__ sorted_pts) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int cell = cell_of[static_cast<long long>(b) * n + i];
   const int pos = atomicAdd(cursor + static_cast<long long>(b) * G_MAX + cell, 1);
   sorted[static_cast<long long>(b) * n + pos] = i;
+  const float *p = xyz + (static_cast<long long>(b) * n + i) * ld;
+  sorted_pts[static_cast<long long>(b) * n + pos] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __int_as_float(i));
 }
 
 __global__ void __launch_bounds__(Q_WARPS * 32)
 bq_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int ld, int n, int m, float radius2,
                 int nsample, const GridMeta *__restrict__ meta, const int *__restrict__ start,
-                const int *__restrict__ sorted, int *__restrict__ idx) {
-  __shared__ int hits[Q_WARPS][Q_CAP];
+                const float4 *__restrict__ sorted, int *__restrict__ idx) {
+  __shared__ int hits[Q_WARPS][Q_SORT];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * Q_WARPS + warp;
   if (j >= m) return;
@@ -194,9 +199,9 @@ bq_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz
         int k = -1;
         bool hit = false;
         if (t < s1) {
-          k = __ldg(sorted + t);
-          const float *p = xyz + static_cast<long long>(k) * ld;
-          hit = bd::sqdist_ref(cx, cy, cz, __ldg(p), __ldg(p + 1), __ldg(p + 2)) < radius2;
+          const float4 q = __ldg(sorted + t);
+          k = __float_as_int(q.w);
+          hit = bd::sqdist_ref(cx, cy, cz, q.x, q.y, q.z) < radius2;
         }
         const unsigned ballot = __ballot_sync(0xFFFFFFFFu, hit);
         if (ballot) {
@@ -230,18 +235,40 @@ bq_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz
     for (int s = min(c2, nsample) + lane; s < nsample; s += 32) row[s] = first;
     return;
   }
-  // rank selection: hit i goes to slot #{hits with a smaller index}; slots >= nsample are dropped
   int first = 0x7FFFFFFF;
-  for (int i = lane; i < cnt; i += 32) {
-    const int ki = h[i];
-    int rank = 0;
-    for (int q = 0; q < cnt; ++q) rank += (h[q] < ki);
-    if (rank < nsample) row[rank] = ki;
-    first = min(first, ki);
-  }
+  if (cnt <= 64) {
+    // rank selection: hit i goes to slot #{hits with a smaller index}; slots >= nsample are dropped
+    for (int i = lane; i < cnt; i += 32) {
+      const int ki = h[i];
+      int rank = 0;
+      for (int q = 0; q < cnt; ++q) rank += (h[q] < ki);
+      if (rank < nsample) row[rank] = ki;
+      first = min(first, ki);
+    }
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, off));
-  if (cnt == 0) first = 0;
+    for (int off = 16; off >= 1; off >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, off));
+    if (cnt == 0) first = 0;
+  } else {
+    // many hits: warp-wide bitonic sort of the (padded) list in shared memory, O(n log^2 n / 32)
+    // instead of the O(n^2 / 32) rank count; the first nsample entries are the answer
+    int n2 = 128;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = cnt + lane; i < n2; i += 32) h[i] = 0x7FFFFFFF;
+    __syncwarp();
+    for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < (n2 >> 1); i += 32) {
+          const int l = 2 * j * (i / j) + (i % j), r = l + j;  // j is a power of two: shifts after unswitching
+          const int a = h[l], c = h[r];
+          const bool up = (l & k2) == 0;
+          if ((a > c) == up) { h[l] = c; h[r] = a; }
+        }
+        __syncwarp();
+      }
+    }
+    for (int s = lane; s < nsample && s < cnt; s += 32) row[s] = h[s];
+    first = h[0];
+  }
   for (int s = min(cnt, nsample) + lane; s < nsample; s += 32) row[s] = first;
 }
 
@@ -249,7 +276,8 @@ bq_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz
 
 extern "C" long long bd_ball_query_grid_workspace_bytes(int B, int n) {
   // meta | count/start (G_MAX+1) | cursor (G_MAX) | cell_of (n) | sorted (n)   per scene, ints
-  return static_cast<long long>(B) * (sizeof(GridMeta) + sizeof(int) * (2LL * G_MAX + 1 + 2LL * n) + 32) + 64;
+  // + (x, y, z, index) records in cell order (16-byte aligned)
+  return static_cast<long long>(B) * (sizeof(GridMeta) + sizeof(int) * (2LL * G_MAX + 1 + 2LL * n) + 32 + 16LL * n) + 96;
 }
 
 namespace {
@@ -257,6 +285,7 @@ struct GridWs {
   GridMeta *meta;
   int *count, *cursor, *cell_of, *sorted;
   unsigned *bbox;
+  float4 *sorted_pts;
 };
 GridWs grid_ws(void *workspace, int B, int n) {
   unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -267,6 +296,8 @@ GridWs grid_ws(void *workspace, int B, int n) {
   g.cell_of = g.cursor + static_cast<size_t>(B) * G_MAX;
   g.sorted = g.cell_of + static_cast<size_t>(B) * n;
   g.bbox = reinterpret_cast<unsigned *>(g.sorted + static_cast<size_t>(B) * n);
+  uintptr_t a = reinterpret_cast<uintptr_t>(g.bbox + static_cast<size_t>(B) * 8);
+  g.sorted_pts = reinterpret_cast<float4 *>((a + 15) & ~static_cast<uintptr_t>(15));
   return g;
 }
 }  // namespace
@@ -287,7 +318,7 @@ extern "C" int bd_grid_build(const float *xyz, int ld_xyz, int B, int n, float r
   dim3 pgrid(bd::ceil_div(n, 256), B);
   bq_count_kernel<<<pgrid, 256, 0, s>>>(xyz, ld_xyz, n, g.meta, g.cell_of, g.count);
   bq_scan_kernel<<<B, 1024, 0, s>>>(g.count, g.cursor, g.meta);
-  bq_fill_kernel<<<pgrid, 256, 0, s>>>(n, g.cell_of, g.cursor, g.sorted);
+  bq_fill_kernel<<<pgrid, 256, 0, s>>>(xyz, ld_xyz, n, g.cell_of, g.cursor, g.sorted, g.sorted_pts);
   BD_CHECK_LAUNCH("bd_grid_build");
   return BD_OK;
 }
@@ -304,7 +335,7 @@ extern "C" int bd_ball_query_grid_query(const float *new_xyz, const float *xyz, 
   const GridWs g = grid_ws(workspace, B, n);
   dim3 qgrid(bd::ceil_div(m, Q_WARPS), B);
   bq_query_kernel<<<qgrid, Q_WARPS * 32, 0, bd::as_stream(stream)>>>(new_xyz, xyz, ld_xyz, n, m, radius * radius, nsample,
-                                                                      g.meta, g.count, g.sorted, idx);
+                                                                      g.meta, g.count, g.sorted_pts, idx);
   BD_CHECK_LAUNCH("bd_ball_query_grid_query");
   return BD_OK;
 }
