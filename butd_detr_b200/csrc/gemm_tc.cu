@@ -354,30 +354,32 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
     const int ldt = NC + 4;
     float *tile = reinterpret_cast<float *>(smem);
 
-    // LayerNorm epilogue: one warp per row, lane owns columns lane + 32 i (N <= 320), LN_ROWS rows
-    // per round.  The residual rows of round 0 are requested now, before the accumulator is
-    // ready, and those of round k + 1 while round k is reduced: their latency is off the path.
-    constexpr int LN_ROWS = 4, LN_ROUNDS = TC_BM / (TC_WARPS * LN_ROWS);
-    float gam[LN_EPI ? 10 : 1], bet[LN_EPI ? 10 : 1], xa[LN_EPI ? LN_ROWS : 1][10], xb[LN_EPI ? LN_ROWS : 1][10];
-    auto ln_load = [&](int round, float (&x)[LN_EPI ? LN_ROWS : 1][10]) {
+    // LayerNorm epilogue: one warp per row, lane owns the float4 column groups lane + 32 i
+    // (N <= 320, N % 4 == 0: at most 3 per lane), LN_ROWS rows per round.  The residual rows of round
+    // 0 are requested now, before the accumulator is ready, and those of round k + 1 while round
+    // k is reduced: their latency is off the path.
+    constexpr int LN_ROWS = 4, LN_ROUNDS = TC_BM / (TC_WARPS * LN_ROWS), LN_V = 3;
+    const int nv = p.N >> 2;  // float4 groups per row
+    float4 gam[LN_EPI ? LN_V : 1], bet[LN_EPI ? LN_V : 1], xa[LN_EPI ? LN_ROWS : 1][LN_V], xb[LN_EPI ? LN_ROWS : 1][LN_V];
+    auto ln_load = [&](int round, float4 (&x)[LN_EPI ? LN_ROWS : 1][LN_V]) {
 #pragma unroll
       for (int u = 0; u < LN_ROWS; ++u) {
         const int r = warp + (round * LN_ROWS + u) * TC_WARPS, gr = row0 + r;
         const bool rok = gr < p.M;
-        const float *res = p.R + (rok ? static_cast<long long>(gr) * p.ldr : 0);
+        const float4 *res = reinterpret_cast<const float4 *>(p.R + (rok ? static_cast<long long>(gr) * p.ldr : 0));
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int col = lane + i * 32;
-          x[u][i] = (rok && col < p.N) ? __ldg(res + col) : 0.f;
+        for (int i = 0; i < LN_V; ++i) {
+          const int v = lane + i * 32;
+          x[u][i] = (rok && v < nv) ? __ldg(res + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
     if (LN_EPI) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int col = lane + i * 32;
-        gam[i] = col < p.N ? __ldg(p.gamma + col) : 0.f;
-        bet[i] = col < p.N ? __ldg(p.beta + col) : 0.f;
+      for (int i = 0; i < LN_V; ++i) {
+        const int v = lane + i * 32;
+        gam[i] = v < nv ? __ldg(reinterpret_cast<const float4 *>(p.gamma) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bet[i] = v < nv ? __ldg(reinterpret_cast<const float4 *>(p.beta) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       ln_load(0, xa);
     }
@@ -460,36 +462,47 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
       }
     } else {
       const float inv_n = 1.0f / static_cast<float>(p.N);
-      auto ln_rows = [&](int round, float (&x)[LN_EPI ? LN_ROWS : 1][10]) {
+      auto ln_rows = [&](int round, float4 (&x)[LN_EPI ? LN_ROWS : 1][LN_V]) {
+        // sum and sum of squares of x = residual + (acc + bias) in one sweep, reduced together by
+        // one round of shuffles; variance = E[x^2] - mean^2 (fp32: the rows are O(1), |mean| << 1e3)
+        float sum[LN_ROWS], sq[LN_ROWS];
+#pragma unroll
+        for (int u = 0; u < LN_ROWS; ++u) {
+          const int r = warp + (round * LN_ROWS + u) * TC_WARPS;
+          const float4 *t4 = reinterpret_cast<const float4 *>(tile + r * ldt);
+          sum[u] = sq[u] = 0.f;
+#pragma unroll
+          for (int i = 0; i < LN_V; ++i) {
+            const int v = lane + i * 32;
+            if (v < nv) {
+              const float4 t = t4[v];
+              x[u][i].x += t.x, x[u][i].y += t.y, x[u][i].z += t.z, x[u][i].w += t.w;
+            }
+            sum[u] += (x[u][i].x + x[u][i].y) + (x[u][i].z + x[u][i].w);
+            sq[u] = fmaf(x[u][i].x, x[u][i].x, fmaf(x[u][i].y, x[u][i].y, fmaf(x[u][i].z, x[u][i].z, fmaf(x[u][i].w, x[u][i].w, sq[u]))));
+          }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+          for (int u = 0; u < LN_ROWS; ++u) {
+            sum[u] += __shfl_xor_sync(0xFFFFFFFFu, sum[u], off);
+            sq[u] += __shfl_xor_sync(0xFFFFFFFFu, sq[u], off);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < LN_ROWS; ++u) {
           const int r = warp + (round * LN_ROWS + u) * TC_WARPS, gr = row0 + r;
           if (gr >= p.M) continue;
-          float sum = 0.f;
+          const float mean = sum[u] * inv_n;
+          const float rstd = rsqrtf(fmaxf(sq[u] * inv_n - mean * mean, 0.f) + p.eps);
+          float4 *y = reinterpret_cast<float4 *>(p.Y + static_cast<long long>(gr) * p.ldy);
 #pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const int col = lane + i * 32;
-            if (col < p.N) x[u][i] += tile[r * ldt + col];
-            sum += x[u][i];
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
-          const float mean = sum * inv_n;
-          float sq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const int col = lane + i * 32;
-            const float d = col < p.N ? x[u][i] - mean : 0.f;
-            sq = fmaf(d, d, sq);
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
-          const float rstd = rsqrtf(sq * inv_n + p.eps);
-          float *y = p.Y + static_cast<long long>(gr) * p.ldy;
-#pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const int col = lane + i * 32;
-            if (col < p.N) y[col] = (x[u][i] - mean) * rstd * gam[i] + bet[i];
+          for (int i = 0; i < LN_V; ++i) {
+            const int v = lane + i * 32;
+            if (v < nv)
+              y[v] = make_float4((x[u][i].x - mean) * rstd * gam[i].x + bet[i].x, (x[u][i].y - mean) * rstd * gam[i].y + bet[i].y,
+                                 (x[u][i].z - mean) * rstd * gam[i].z + bet[i].z, (x[u][i].w - mean) * rstd * gam[i].w + bet[i].w);
           }
         }
       };
@@ -652,6 +665,10 @@ extern "C" int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda
   if (rc != BD_OK) return rc;
   BD_REQUIRE(R && gamma && beta && ldr >= N, "bd_linear_ln_tc: null pointer / bad ldr");
   BD_REQUIRE(n_sub * BN >= N && N <= 320, "bd_linear_ln_tc: one CTA must own complete rows (N <= n_sub*BN, N <= 320)");
+  BD_REQUIRE(N % 4 == 0 && ldr % 4 == 0 && ldy % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(gamma) |
+                   reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+             "bd_linear_ln_tc: N, ldr, ldy must be multiples of 4 and R, Y, gamma, beta 16-byte aligned");
   LinearTcParams p = {};
   p.A = A, p.A2 = A2, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y;
   p.R = R, p.gamma = gamma, p.beta = beta, p.eps = eps, p.ldr = ldr;

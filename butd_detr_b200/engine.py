@@ -292,7 +292,7 @@ class ForwardEngine:
         W, b = self.W[key]
         M, K = x.shape
         N = W.shape[0]
-        if (self.precision == "fp32" or N > 320 or K % 8 or x.stride(0) % 4 or x.data_ptr() % 16 or
+        if (self.precision == "fp32" or N > 320 or N % 4 or K % 8 or x.stride(0) % 4 or x.data_ptr() % 16 or
                 (add is not None and (add.stride(0) % 4 or add.data_ptr() % 16))):
             return self.add_ln(self.lin(x, key, add=add), res, ln_key, eps)
         assert x.stride(1) == 1 and W.shape[1] == K and res.is_contiguous() and res.shape == (M, N)

@@ -6,7 +6,7 @@ from butd_detr_b200.engine import pack_weight_tc
 lib = _lib.load()
 dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
 lib.bd_linear_tc_set_debug(dbg.data_ptr())
-for (M, N, K, ln, split) in [(8192, 288, 288, 0, 3), (8192, 288, 288, 1, 3), (8192, 288, 288, 2, 3), (32768, 576, 288, 0, 3)]:
+for (M, N, K, ln, split) in [(65536, 288, 288, 1, 1), (65536, 288, 288, 1, 3), (65536, 576, 288, 0, 1)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / math.sqrt(K); b = torch.randn(N, device="cuda")
     Y = torch.empty(M, N, device="cuda"); R = torch.randn(M, N, device="cuda"); g_ = torch.ones(N, device="cuda")
     Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, split, full_rows=(ln == 1), wide=(ln == 0))
