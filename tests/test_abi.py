@@ -52,3 +52,18 @@ def test_sass_uses_cluster_and_async_instructions():
     assert "REDUX" in sass   # warp reductions (CREDUX.MAX on sm_100)
     assert "STAS" in sass    # st.async into peer CTAs' shared memory
     assert "SYNCS" in sass   # mbarrier arrive / try_wait
+
+
+def test_sass_uses_blackwell_tensor_and_tma_instructions():
+    """The tensor-core kernels must really be tcgen05 / TMEM / TMA code (B200_PROFILING.md: the PTX
+    names never appear in SASS): UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG =
+    cp.async.bulk.tensor (activations of the linear kernel), UBLKCP = cp.async.bulk (weights, K/V
+    tiles, write-out), and no legacy mma.sync (HMMA) anywhere."""
+    import subprocess
+    from butd_detr_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA" not in sass
+    # griddepcontrol.wait / launch_dependents of the programmatic dependent launches
+    assert "ACQBULK" in sass or "PREEXIT" in sass or "DEPBAR" in sass
