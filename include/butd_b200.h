@@ -152,17 +152,18 @@ int bd_linear_f32(const float *A, int lda, const float *A2, int lda2, const floa
                   const float *bias, float *Y, int ldy, int M, int N, int K, int relu,
                   bd_stream_t stream);
 
-/* Same contract as bd_linear_f32, computed on the 5th-gen tensor cores (tcgen05.mma, bf16
- * operands, fp32 accumulation in TMEM).  A is converted to bf16 while it is staged; `Wp` is the
- * weight pre-packed by the host (butd_detr_b200.engine.pack_weight_tc) into the kernel's shared
- * memory layout:  Wp[n_group][k_chunk][part][sub][BN/8][KC/8][8 rows][8 k] bf16, zero padded,
- * where one CTA computes n_sub consecutive BN-wide column tiles (n_group = n / (n_sub*BN),
- * sub = (n / BN) % n_sub) and k_chunk = k / KC.  KC: multiple of 16; BN: multiple of 16, <= 256;
- * n_sub * BN <= 512 (TMEM columns).
- * split = 1: plain bf16 operands (part = {hi}).  split = 3 ("bf16x3"): every fp32 operand is
- * carried as bf16 hi + bf16 lo and D += Ahi*Whi + Alo*Whi + Ahi*Wlo (part = {hi, lo}), which
- * restores fp32-grade products on the bf16 tensor pipe.  Two pipeline stages of
- * parts * (128 + n_sub*BN) * KC * 2 bytes must fit 226 KB of shared memory. */
+/* Same contract as bd_linear_f32, computed on the 5th-gen tensor cores (tcgen05.mma, 16-bit
+ * operands, fp32 accumulation in TMEM).  A (and A2) arrive through the TMA unit as raw fp32
+ * chunks and are converted while staged; `Wp` is the weight pre-packed by the host
+ * (butd_detr_b200.engine.pack_weight_tc) into the kernel's shared-memory layout (128-byte swizzle,
+ * K-major):  Wp[n_group][k_chunk][part][sub][BN rows][64 k] 16-bit, zero padded, where one CTA
+ * computes n_sub consecutive BN-wide column tiles (n_group = n / (n_sub*BN), sub = (n / BN) %
+ * n_sub) and k_chunk = k / 64.  KC = 64; BN: multiple of 16, <= 256; n_sub * BN <= 512 (TMEM
+ * columns).
+ * split = 1: FP16 operands (part = {fp16(W)}), one MMA per product — outputs of the whole forward
+ * within the 1e-2 gate.  split = 3 ("bf16x3"): every fp32 operand is carried as bf16 hi + bf16 lo
+ * and D += Ahi*Whi + Alo*Whi + Ahi*Wlo (part = {hi, lo}), which restores fp32-grade products on
+ * the bf16 tensor pipe (1e-3 gate).  Two pipeline stages must fit 217 KB of shared memory. */
 int bd_linear_tc(const float *A, int lda, const float *A2, int lda2, const void *Wp,
                  const float *bias, float *Y, int ldy, int M, int N, int K, int KC, int n_chunks,
                  int BN, int n_sub, int relu, int split, bd_stream_t stream);
@@ -227,10 +228,11 @@ int bd_attention_f32(const float *Q, int ldq, long long sq_b, const float *K, in
                      int B, int H, int Lq, int Lk, int hd, float scale, bd_stream_t stream);
 
 /* Same contract as bd_attention_f32 on the tensor cores (tcgen05.mma, accumulators in TMEM, exact
- * online softmax in fp32).  head_dim 36 only; Q / K rows 16-byte aligned.  split = 1: bf16
+ * online softmax in fp32).  head_dim 36 only; Q / K rows 16-byte aligned.  split = 1: fp16
  * operands; split = 3: bf16 hi/lo split operands for Q·Kᵀ and P·V (fp32-grade).  `workspace`:
  * bd_attention_tc_workspace_bytes(...) bytes of device scratch (16-byte aligned) that receives the
- * packed bf16 operand tiles (a pack kernel runs first, then the tensor-core kernel). */
+ * packed 16-bit K / Vᵀ operand tiles (a pack kernel runs first, then the tensor-core kernel,
+ * which converts its own Q rows). */
 long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int split);
 int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk,
                     long long sk_b, const float *V, int ldv, long long sv_b,
