@@ -128,6 +128,10 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (set before torch / the C
+    # oracle initialise their OpenMP runtimes)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["MKL_NUM_THREADS"] = str(threads)
     times = cpu_reference_forward(args.warmup + args.steps, threads)[args.warmup:]
     per = sum(times) / len(times)
     val = 1.0 / per
@@ -366,7 +370,7 @@ def main():
         del m2
 
     cpu_baseline = None
-    if rank == 0 and args.cpu_scenes > 0:
+    if rank == 0 and world == 1 and args.cpu_scenes > 0:  # the CPU arm is timed at N = 1 only
         threads = os.cpu_count()
         times = cpu_reference_forward(args.cpu_scenes + 1, threads)[1:]
         cpu_baseline = {"value": len(times) / sum(times), "unit": "scenes/s", "cores": threads, "kind": "port",
