@@ -692,8 +692,10 @@ class ForwardEngine:
                     mem_kv.append((kv_l, kv_d, kv_v, kvs.record_event()))
             ep["text_memory"] = text.view(B, L, E)
             ep["seed_features"] = vis.view(B, V, E).transpose(1, 2)
-            if cfg["contrastive_align_loss"]:
-                ep["proj_tokens"] = self.contrastive(text, "text", B, L)
+            if cfg["contrastive_align_loss"]:  # nothing downstream reads it: off the critical path
+                self.head_stream.wait_event(main.record_event())
+                with torch.cuda.stream(self.head_stream):
+                    ep["proj_tokens"] = self.contrastive(text, "text", B, L)
             # ---- query generation (models/bdetr.py:177-191)
             h = self.lin(vis, "points_obj_cls.conv1", relu=True)
             h = self.lin(h, "points_obj_cls.conv2", relu=True)
