@@ -23,7 +23,8 @@ _SIGNATURES = {
     "bd_fps_set_cluster": [_I],
     "bd_set_pdl": [_I],
     "bd_linear_tc_set_occupancy": [_I],
-    "bd_fps_ordered": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "bd_fps_grid": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "bd_fps_grid_set_warps": [_I],
     "bd_grid_build": [_P, _I, _I, _I, _F, _P, _P],
     "bd_ball_query_grid_query": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P],
     "bd_gather_points": [_P, _P, _I, _I, _I, _I, _P, _P],
@@ -58,6 +59,7 @@ _SIGNATURES = {
 }
 
 EXPORTED = sorted(list(_SIGNATURES) + ["bd_version", "bd_last_error", "bd_arch", "bd_fps_resident_capacity",
+                                            "bd_fps_grid_capacity", "bd_fps_grid_scratch_bytes",
                                             "bd_attention_tc_workspace_bytes", "bd_ball_query_grid_workspace_bytes",
                                             "bd_attention_tc_select", "bd_grid_order"])
 
@@ -83,6 +85,9 @@ def load():
     lib.bd_last_error.restype = ctypes.c_char_p
     lib.bd_arch.restype = ctypes.c_char_p
     lib.bd_fps_resident_capacity.restype = _I
+    lib.bd_fps_grid_capacity.restype = _I
+    lib.bd_fps_grid_scratch_bytes.restype = _LL
+    lib.bd_fps_grid_scratch_bytes.argtypes = [_I, _I]
     lib.bd_ball_query_grid_workspace_bytes.restype = _LL
     lib.bd_ball_query_grid_workspace_bytes.argtypes = [_I, _I]
     lib.bd_attention_tc_workspace_bytes.restype = _LL

@@ -699,18 +699,14 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
   p.Kp = p.Qp + static_cast<size_t>(B) * H * p.nq * parts * QK_PART;
   p.Vp = p.Kp + static_cast<size_t>(B) * H * p.nk * parts * k_part(BK);
   constexpr size_t WS_SMEM1 = 2 * (QK_PART + k_part(128) + v_part(128)) + 1024, WS_SMEM2 = 2 * WS_SMEM1 - 1024;
-  static thread_local bool configured = false;
-  if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024),
-            "bd_attention_tc");
-    BD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024),
-            "bd_attention_tc");
-    BD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1),
-            "bd_attention_tc");
-    BD_CUDA(cudaFuncSetAttribute(attention_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2),
-            "bd_attention_tc");
-    configured = true;
-  }
+  static bd::PerDeviceOnce configured;  // function attributes are per device
+  BD_CUDA(configured.run([&]() {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<1, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2);
+    return e;
+  }), "bd_attention_tc");
   cudaStream_t s = bd::as_stream(stream);
   dim3 pgrid(p.nq + 2 * p.nk, H, B), grid(p.nq, H, B), wgrid(bd::ceil_div(p.nq, 2), H, B);
   if (impl == 1) {

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/butd_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -16,8 +18,30 @@ void set_error(const char *fmt, ...);
 
 inline cudaStream_t as_stream(bd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Number of SMs of the current device (cached per thread).
+// Number of SMs of the current device (cached per device).
 int sm_count();
+
+// One-time per-DEVICE set-up of a kernel (cudaFuncSetAttribute is a per-device property: a process
+// that moves to a second GPU must opt that device in as well).  run(f) calls f() the first time it
+// is reached with a given current device and remembers success.
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0ull;
+  template <class F>
+  cudaError_t run(F &&f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> guard(mu);
+    if (done & bit) return cudaSuccess;
+    const cudaError_t e = f();
+    if (e == cudaSuccess) done |= bit;
+    return e;
+  }
+};
+
+// (x, y, z, bits(index)) records of the cell list built by bd_grid_build, in cell order (B, n)
+const float4 *grid_sorted_points(void *grid_workspace, int B, int n);
 
 #define BD_REQUIRE(cond, ...)            \
   do {                                   \

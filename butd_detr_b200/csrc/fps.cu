@@ -2,33 +2,39 @@
 // (/root/reference/pointnet2/_ext_src/src/sampling_gpu.cu:74-234).
 //
 // Design (B200-first, not a translation):
-//   * one thread-block CLUSTER (1, 8 or 16 CTAs x 512 threads) per scene; every point and its
-//     running min-distance live in REGISTERS for the whole kernel (the reference re-reads
-//     xyz and read-modify-writes `temp` in global memory 2047 times);
-//   * per round: register update -> 2x REDUX per warp -> one CTA barrier -> 2x REDUX ->
-//     one st.async all-to-all over distributed shared memory with an mbarrier (complete_tx)
-//     per CTA -> 2x REDUX.  No cluster.sync, no global memory traffic inside the loop;
 //   * the reference's tie-breaking is an artefact of its launch geometry (thread t scans
 //     k = t, t+bs, ... with a strict '>' and the shared-memory tree keeps the lower slot):
 //     among equal maxima the winner has the smallest bit-reversed (k mod bs), then the
-//     smallest k.  Points are therefore laid out by that RANK = brev(k mod bs) * Q + k / bs
-//     and the reduction key is (distance bits, ~rank), which reproduces the reference's
-//     choice exactly for any decomposition into threads / warps / CTAs.
+//     smallest k.  Every point therefore carries RANK = brev(k mod bs) * Q + k / bs and the
+//     reduction key is (distance bits, ~rank), which reproduces the reference's choice exactly
+//     for any decomposition into threads / warps / CTAs / buckets.
+//
+// Two kernels share that key:
+//   * fps_resident_kernel — latency mode (bd_fps): one thread-block CLUSTER (1, 4, 8 or 16 CTAs x 512
+//     threads) per scene; every point and its running min-distance live in REGISTERS for the whole
+//     kernel (the reference re-reads xyz and read-modify-writes `temp` in global memory 2047
+//     times); per round: register sweep -> 2x REDUX per warp -> one CTA barrier -> 2x REDUX -> one
+//     st.async all-to-all over distributed shared memory with an mbarrier (complete_tx) per CTA ->
+//     2x REDUX.  No cluster.sync, no global memory traffic inside the loop.  It owns whole SMs
+//     (register file), so a wave holds 37 scenes of 50k points.
+//   * fps_bucket_kernel — throughput mode (bd_fps_grid): ONE CTA per scene.  The points are taken in
+//     the cell-list order of bd_grid_build and cut into buckets of 32 consecutive records; the state
+//     of a bucket (bounding box, its current farthest point and that point's key) lives in the
+//     registers of one lane.  A bucket whose box is farther from the new sample than the bucket's
+//     largest running distance cannot change and is skipped, so a round reads ~2 % of the cloud (from
+//     L2, 20 bytes per point) instead of sweeping all of it; a whole batch of up to 148 scenes runs in
+//     ONE wave with a small footprint per SM.  Distances, minima and keys are computed by the same
+//     expressions as in the resident kernel: the indices are identical, bit for bit.
 #include "common.cuh"
 
 #include <cmath>
 
 namespace {
 
-__device__ unsigned long long g_fps_dbg[32];  // FPS_DEBUG_COUNT: [0] thread sweeps, [1] warp sweeps, [2] thread rounds, [3] warp rounds
-#ifdef FPS_DEBUG_COUNT
-#define FPS_STAMP(i) do { if (blockIdx.x == 0 && tid == 0 && j == 1000) g_fps_dbg[8 + (i)] = clock64(); } while (0)
-#else
-#define FPS_STAMP(i) do { } while (0)
-#endif
 constexpr int FPS_THREADS = 512;
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 constexpr int MSG_BYTES = 24;  // 16-byte + 8-byte st.async per source CTA and round
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -87,18 +93,19 @@ __device__ __forceinline__ int rank_to_k(int r, int Q, int log2bs, int N) {
   const int k = q * bs + t;
   return k < N ? k : -1;
 }
+// the reference's rank of point k; padding (k < 0) sorts last
+__device__ __forceinline__ uint32_t rank_of_k(int k, int Q, int log2bs) {
+  if (k < 0) return 0xFFFFFFFFu;
+  const uint32_t trev = log2bs ? (__brev(static_cast<uint32_t>(k & ((1 << log2bs) - 1))) >> (32 - log2bs)) : 0u;
+  return trev * static_cast<uint32_t>(Q) + static_cast<uint32_t>(k >> log2bs);
+}
+// reduction key of a running distance: 0 = not selectable (skipped point / padding)
+__device__ __forceinline__ uint32_t dist_key(float t) { return t < 0.f ? 0u : __float_as_uint(t) + 1u; }
 
-// ORDERED: the points are taken in the order given by `order` (a permutation of 0..N-1 per scene
-// that keeps spatial neighbours together — the cell-list order of bd_grid_build) instead of rank
-// order.  A thread's P points then sit in a small box, and a round whose new sample lies farther
-// from that box than the thread's largest running distance cannot change any of them: the thread
-// skips its sweep and re-submits its cached candidate.  After the first ~100 samples a few per cent
-// of the threads are active per round, and the kernel is bound by the reduction chain alone.  The
-// result is unchanged: the reduction key still carries the reference's rank of each point.
-template <int CLUSTER, int P, bool ORDERED>
+template <int CLUSTER, int P>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, int N, int m, int log2bs, int Q,
-                    const int *__restrict__ order, int *__restrict__ idx_out) {
+                    int *__restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   float4 *pts = reinterpret_cast<float4 *>(dyn_smem);  // [FPS_THREADS * P] : x, y, z, bits(k)
   __shared__ uint2 wpart[2][FPS_WARPS];
@@ -125,65 +132,21 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
   const int cta_base = static_cast<int>(crank) * FPS_THREADS * P;
   const int base_rank = cta_base + tid * P;
   float px[P], py[P], pz[P], tmin[P];
-  float bx0 = INFINITY, by0 = INFINITY, bz0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY, bz1 = -INFINITY;
-  const int bs_mask = (1 << log2bs) - 1;
-  auto rank_of = [&](int k) -> uint32_t {  // the reference's rank of point k; padding sorts last
-    if (k < 0) return 0xFFFFFFFFu;
-    const uint32_t trev = log2bs ? (__brev(static_cast<uint32_t>(k & bs_mask)) >> (32 - log2bs)) : 0u;
-    return trev * static_cast<uint32_t>(Q) + static_cast<uint32_t>(k >> log2bs);
-  };
-  if (ORDERED) {
-    // positions base_rank .. base_rank + P - 1 of the spatial order; the thread's own P entries
-    // are then sorted by rank (in its private slice of `pts`), so that "first maximum" inside the
-    // thread is the smallest rank, as the key comparison across threads requires
-    order += static_cast<long long>(scene) * N;
-    float4 *mine = pts + tid * P;
-    for (int i = 0; i < P; ++i) {
-      const int k = base_rank + i < N ? __ldg(order + base_rank + i) : -1;
-      float4 e = make_float4(0.f, 0.f, 0.f, __int_as_float(k));
-      if (k >= 0) {
-        const float *p = xyz + static_cast<long long>(k) * ld;
-        e.x = __ldg(p), e.y = __ldg(p + 1), e.z = __ldg(p + 2);
-      }
-      const uint32_t key = rank_of(k);
-      int q = i - 1;
-      while (q >= 0 && rank_of(__float_as_int(mine[q].w)) > key) {
-        mine[q + 1] = mine[q];
-        --q;
-      }
-      mine[q + 1] = e;
-    }
-  }
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    int k;
+    const int k = rank_to_k(base_rank + i, Q, log2bs, N);
     float x = 0.f, y = 0.f, z = 0.f;
-    if (ORDERED) {
-      const float4 e = pts[tid * P + i];
-      x = e.x, y = e.y, z = e.z, k = __float_as_int(e.w);
-    } else {
-      k = rank_to_k(base_rank + i, Q, log2bs, N);
-    }
     bool valid = k >= 0;
     if (valid) {
-      if (!ORDERED) {
-        const float *p = xyz + static_cast<long long>(k) * ld;
-        x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-      }
+      const float *p = xyz + static_cast<long long>(k) * ld;
+      x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
       const float mag = bd::sqnorm_ref(x, y, z);
       valid = !(static_cast<double>(mag) <= 1e-3);  // sampling_gpu.cu:105-106 (double compare)
     }
     px[i] = x, py[i] = y, pz[i] = z;
     tmin[i] = valid ? 1e10f : -2.0f;  // -2 never beats the initial best of -1 and min() keeps it
-    if (!ORDERED) pts[tid * P + i] = make_float4(x, y, z, __int_as_float(k));
-    if (ORDERED && valid) {
-      bx0 = fminf(bx0, x), by0 = fminf(by0, y), bz0 = fminf(bz0, z);
-      bx1 = fmaxf(bx1, x), by1 = fmaxf(by1, y), bz1 = fmaxf(bz1, z);
-    }
+    pts[tid * P + i] = make_float4(x, y, z, __int_as_float(k));
   }
-  float best = -1.0f;  // ORDERED: cached across rounds while the thread's points are untouched
-  int bi = 0;
-  uint32_t lo_cached = 0u;
   const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
   float x1 = x0, y1 = y0, z1 = z0;
   if (crank == 0 && tid == 0) idx_out[0] = 0;
@@ -192,72 +155,24 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
   uint32_t phase_bits = 0;
   for (int j = 1; j < m; ++j) {
     const int p = j & 1;
-    FPS_STAMP(0);
-    bool sweep = true;
-    if (ORDERED) {
-      // lower bound of the distance from the new sample to the thread's box; 1e-5 covers the
-      // rounding of both this bound and the kernel's distance expression
-      const float ex = fmaxf(fmaxf(bx0 - x1, x1 - bx1), 0.f), ey = fmaxf(fmaxf(by0 - y1, y1 - by1), 0.f),
-                  ez = fmaxf(fmaxf(bz0 - z1, z1 - bz1), 0.f);
-      const float lb = fmaf(ez, ez, fmaf(ex, ex, ey * ey));
-      sweep = !(lb * 0.99999f > best) || j == 1;
+    float best = -1.0f;
+    int bi = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float d = bd::sqdist_ref(px[i], py[i], pz[i], x1, y1, z1);
+      const float t = fminf(d, tmin[i]);
+      tmin[i] = t;
+      if (t > best) { best = t; bi = i; }
     }
-#if defined(FPS_DEBUG_COUNT) && FPS_DEBUG_COUNT == 1
-    if (ORDERED) {
-      const unsigned any = __ballot_sync(0xFFFFFFFFu, sweep);
-      if (sweep) atomicAdd(&g_fps_dbg[0], 1ull);
-      if (lane == 0) { atomicAdd(&g_fps_dbg[1], any ? 1ull : 0ull); atomicAdd(&g_fps_dbg[3], 1ull); }
-      atomicAdd(&g_fps_dbg[2], 1ull);
-    }
-#endif
-    if (sweep && !ORDERED) {
-      best = -1.0f;
-      bi = 0;
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        const float d = bd::sqdist_ref(px[i], py[i], pz[i], x1, y1, z1);
-        const float t = fminf(d, tmin[i]);
-        tmin[i] = t;
-        if (t > best) { best = t; bi = i; }
-      }
-    }
-    if (sweep && ORDERED) {
-      // few warps sweep per round, so the sweep is latency- not throughput-bound: the first-maximum
-      // search runs as G independent chains joined by a short tree (left operand wins ties, i.e.
-      // the smaller index — same winner as the sequential scan)
-      constexpr int G = 5, PER = (P + G - 1) / G;
-      float gv[G];
-      int gi[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) gv[g] = -1.0f, gi[g] = 0;
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        const float d = bd::sqdist_ref(px[i], py[i], pz[i], x1, y1, z1);
-        const float t = fminf(d, tmin[i]);
-        tmin[i] = t;
-        if (t > gv[i / PER]) { gv[i / PER] = t; gi[i / PER] = i; }
-      }
-#pragma unroll
-      for (int st = 1; st < G; st *= 2)
-#pragma unroll
-        for (int g = 0; g + st < G; g += 2 * st)
-          if (gv[g + st] > gv[g]) { gv[g] = gv[g + st]; gi[g] = gi[g + st]; }
-      best = gv[0], bi = gi[0];
-      lo_cached = 0xFFFFFFFFu - rank_of(__float_as_int(pts[tid * P + bi].w));
-    }
-    FPS_STAMP(1);
-    const uint32_t hi = best < 0.f ? 0u : __float_as_uint(best) + 1u;
-    const uint32_t lo = ORDERED ? lo_cached : 0xFFFFFFFFu - static_cast<uint32_t>(base_rank + bi);
-    const uint32_t whi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    const uint32_t wlo = __reduce_max_sync(0xFFFFFFFFu, hi == whi ? lo : 0u);
+    const uint32_t hi = dist_key(best);
+    const uint32_t lo = 0xFFFFFFFFu - static_cast<uint32_t>(base_rank + bi);
+    const uint32_t whi = __reduce_max_sync(FULL, hi);
+    const uint32_t wlo = __reduce_max_sync(FULL, hi == whi ? lo : 0u);
     if (lane == 0) wpart[p][warp] = make_uint2(whi, wlo);
-    FPS_STAMP(2);
     __syncthreads();
-    FPS_STAMP(3);
     const uint2 w = lane < FPS_WARPS ? wpart[p][lane] : make_uint2(0u, 0u);
-    const uint32_t chi = __reduce_max_sync(0xFFFFFFFFu, w.x);
-    const uint32_t clo = __reduce_max_sync(0xFFFFFFFFu, w.x == chi ? w.y : 0u);
-    FPS_STAMP(4);
+    const uint32_t chi = __reduce_max_sync(FULL, w.x);
+    const uint32_t clo = __reduce_max_sync(FULL, w.x == chi ? w.y : 0u);
     int k;
     if (CLUSTER == 1) {
       if (chi == 0u) {
@@ -268,21 +183,7 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
       }
       if (tid == 0) idx_out[j] = k;
     } else {
-      if (ORDERED) {
-        // the CTA's winner is the one thread whose key equals the reduced key (ranks are unique):
-        // it knows where its point is and sends the CTA's message itself
-        if (hi == chi && lo == clo && (clo != 0u || tid == 0)) {  // clo == 0: a CTA of padding only
-          float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (chi != 0u) c = pts[tid * P + bi];
-#pragma unroll
-          for (int dst = 0; dst < CLUSTER; ++dst) {
-            const uint32_t dbar = mapa_u32(smem_u32(&bars[p]), dst);
-            st_async_v4(mapa_u32(smem_u32(&slotA[p][crank]), dst), chi, clo, __float_as_uint(c.x),
-                        __float_as_uint(c.y), dbar);
-            st_async_v2(mapa_u32(smem_u32(&slotB[p][crank]), dst), __float_as_uint(c.z), __float_as_uint(c.w), dbar);
-          }
-        }
-      } else if (warp == 0 && lane < CLUSTER) {
+      if (warp == 0 && lane < CLUSTER) {
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (chi != 0u) c = pts[(0xFFFFFFFFu - clo) - cta_base];
         const uint32_t dbar = mapa_u32(smem_u32(&bars[p]), lane);
@@ -290,23 +191,20 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
                     __float_as_uint(c.y), dbar);
         st_async_v2(mapa_u32(smem_u32(&slotB[p][crank]), lane), __float_as_uint(c.z), __float_as_uint(c.w), dbar);
       }
-      FPS_STAMP(5);
       mbar_wait_cluster(smem_u32(&bars[p]), (phase_bits >> p) & 1u);
-      FPS_STAMP(6);
       phase_bits ^= 1u << p;
       const uint4 a = lane < CLUSTER ? slotA[p][lane] : make_uint4(0u, 0u, 0u, 0u);
-      const uint32_t ghi = __reduce_max_sync(0xFFFFFFFFu, a.x);
-      const uint32_t glo = __reduce_max_sync(0xFFFFFFFFu, a.x == ghi ? a.y : 0u);
+      const uint32_t ghi = __reduce_max_sync(FULL, a.x);
+      const uint32_t glo = __reduce_max_sync(FULL, a.x == ghi ? a.y : 0u);
       if (ghi == 0u) {
         x1 = x0, y1 = y0, z1 = z0, k = 0;
       } else {
-        const int e = __ffs(__ballot_sync(0xFFFFFFFFu, lane < CLUSTER && a.x == ghi && a.y == glo)) - 1;
+        const int e = __ffs(__ballot_sync(FULL, lane < CLUSTER && a.x == ghi && a.y == glo)) - 1;
         const uint4 aa = slotA[p][e];
         const uint2 bb = slotB[p][e];
         x1 = __uint_as_float(aa.z), y1 = __uint_as_float(aa.w), z1 = __uint_as_float(bb.x);
         k = static_cast<int>(bb.y);
       }
-      FPS_STAMP(7);
       if (tid == 0) {
         mbar_arrive_expect_tx(smem_u32(&bars[p]), CLUSTER * MSG_BYTES);  // re-arm for round j+2
         if (crank == 0) idx_out[j] = k;
@@ -314,6 +212,153 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
     }
   }
   if (CLUSTER > 1) cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Throughput mode: one CTA per scene over the cell-ordered records of bd_grid_build.
+//   bucket b = records [32 b, 32 b + 32) of the scene; it belongs to warp (b % WARPS), and inside the
+//   warp to lane (q % 32), register slot (q / 32) with q = b / WARPS — consecutive (spatially
+//   adjacent) buckets go to different warps, so the few active buckets of a round spread over the CTA.
+//   `tmin` (B, 32 * ceil(N / 32)) floats: running distances in record order (global scratch; a
+//   bucket's entries are only ever touched by the lanes of its own warp, so no fences are needed).
+// Per round: every lane tests its SLOTS buckets against the new sample (registers only) -> ballot ->
+// the warp visits its active buckets, up to U at a time (loads in flight together): 20 bytes per
+// point from L2, new minima written back only where they changed, 2x REDUX for the bucket's new
+// farthest point -> lane-level maximum over the slots -> 2x REDUX -> ONE CTA barrier -> 2x REDUX.
+template <int WARPS, int SLOTS, int U>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ xyz, int ld, long long bstride, int N,
+                  int m, int log2bs, int Q, float *__restrict__ tmin, int *__restrict__ idx_out) {
+  __shared__ uint2 wkey[2][WARPS];
+  __shared__ float4 wxyz[2][WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int scene = blockIdx.x;
+  const int nb = (N + 31) >> 5;
+  const float4 *pts = records + static_cast<long long>(scene) * N;
+  float *tm = tmin + static_cast<long long>(scene) * nb * 32;
+  xyz += static_cast<long long>(scene) * bstride;
+  idx_out += static_cast<long long>(scene) * m;
+
+  float bx0[SLOTS], by0[SLOTS], bz0[SLOTS], bx1[SLOTS], by1[SLOTS], bz1[SLOTS];  // bucket bounding boxes
+  float cx[SLOTS], cy[SLOTS], cz[SLOTS];                                         // farthest point of the bucket
+  uint32_t hi[SLOTS], lo[SLOTS];                                                 // ... and its key
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    bx0[s] = by0[s] = bz0[s] = bx1[s] = by1[s] = bz1[s] = 0.f;
+    cx[s] = cy[s] = cz[s] = 0.f;
+    hi[s] = lo[s] = 0u;
+    for (int o = 0; o < 32; ++o) {
+      const int b = (s * 32 + o) * WARPS + warp;
+      if (b >= nb) break;  // warp-uniform
+      const int i = (b << 5) + lane;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool valid = i < N;
+      if (valid) {
+        p = __ldg(pts + i);
+        const float mag = bd::sqnorm_ref(p.x, p.y, p.z);
+        valid = !(static_cast<double>(mag) <= 1e-3);  // sampling_gpu.cu:105-106 (double compare)
+      }
+      tm[i] = valid ? 1e10f : -2.0f;
+      float mn[3] = {valid ? p.x : INFINITY, valid ? p.y : INFINITY, valid ? p.z : INFINITY};
+      float mx[3] = {valid ? p.x : -INFINITY, valid ? p.y : -INFINITY, valid ? p.z : -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          mn[c] = fminf(mn[c], __shfl_xor_sync(FULL, mn[c], off));
+          mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL, mx[c], off));
+        }
+      }
+      const bool any = __any_sync(FULL, valid);
+      if (lane == o) {
+        bx0[s] = mn[0], by0[s] = mn[1], bz0[s] = mn[2], bx1[s] = mx[0], by1[s] = mx[1], bz1[s] = mx[2];
+        hi[s] = any ? dist_key(1e10f) : 0u;  // every selectable point starts at 1e10: active in round 1
+      }
+    }
+  }
+  const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
+  float x1 = x0, y1 = y0, z1 = z0;
+  if (tid == 0) idx_out[0] = 0;
+
+  for (int j = 1; j < m; ++j) {
+    const int pp = j & 1;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      bool active = false;
+      if (hi[s] != 0u) {
+        // lower bound of the distance from the sample to the bucket's box, by the kernel's own
+        // distance expression (rounding is monotonic, so it never exceeds a member's distance; the
+        // factor leaves a margin anyway)
+        const float best = __uint_as_float(hi[s] - 1u);
+        const float ex = fmaxf(fmaxf(bx0[s] - x1, x1 - bx1[s]), 0.f), ey = fmaxf(fmaxf(by0[s] - y1, y1 - by1[s]), 0.f),
+                    ez = fmaxf(fmaxf(bz0[s] - z1, z1 - bz1[s]), 0.f);
+        const float lb = fmaf(ez, ez, fmaf(ex, ex, ey * ey));
+        active = !(lb * 0.99999f > best);
+      }
+      unsigned mask = __ballot_sync(FULL, active);
+      while (mask) {
+        int o[U];
+        float4 p[U];
+        float told[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          o[u] = mask ? __ffs(mask) - 1 : -1;
+          mask &= mask - 1u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (o[u] < 0) continue;
+          const int i = (((s * 32 + o[u]) * WARPS + warp) << 5) + lane;
+          p[u] = i < N ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+          told[u] = tm[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (o[u] < 0) continue;
+          const int i = (((s * 32 + o[u]) * WARPS + warp) << 5) + lane;
+          const float d = bd::sqdist_ref(p[u].x, p[u].y, p[u].z, x1, y1, z1);
+          const float t = fminf(d, told[u]);
+          if (t < told[u]) tm[i] = t;
+          const uint32_t h = dist_key(t);
+          const uint32_t wh = __reduce_max_sync(FULL, h);
+          const uint32_t l = (h == wh && wh != 0u) ? 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs) : 0u;
+          const uint32_t wl = __reduce_max_sync(FULL, l);
+          const int src = __ffs(__ballot_sync(FULL, h == wh && l == wl)) - 1;
+          const float wx = __shfl_sync(FULL, p[u].x, src), wy = __shfl_sync(FULL, p[u].y, src),
+                      wz = __shfl_sync(FULL, p[u].z, src);
+          if (lane == o[u]) hi[s] = wh, lo[s] = wl, cx[s] = wx, cy[s] = wy, cz[s] = wz;
+        }
+      }
+    }
+    // farthest point over the lane's buckets, the warp, the CTA
+    uint32_t mh = hi[0], ml = lo[0];
+    float mx = cx[0], my = cy[0], mz = cz[0];
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) {
+      if (hi[s] > mh || (hi[s] == mh && lo[s] > ml)) mh = hi[s], ml = lo[s], mx = cx[s], my = cy[s], mz = cz[s];
+    }
+    const uint32_t wh = __reduce_max_sync(FULL, mh);
+    const uint32_t wl = __reduce_max_sync(FULL, mh == wh ? ml : 0u);
+    const int src = __ffs(__ballot_sync(FULL, mh == wh && (ml == wl || wh == 0u))) - 1;
+    if (lane == src) {
+      wkey[pp][warp] = make_uint2(wh, wl);
+      wxyz[pp][warp] = make_float4(mx, my, mz, 0.f);
+    }
+    __syncthreads();
+    const uint2 w = lane < WARPS ? wkey[pp][lane] : make_uint2(0u, 0u);
+    const uint32_t ch = __reduce_max_sync(FULL, w.x);
+    const uint32_t cl = __reduce_max_sync(FULL, w.x == ch ? w.y : 0u);
+    int k;
+    if (ch == 0u) {
+      x1 = x0, y1 = y0, z1 = z0, k = 0;  // nothing selectable: reference yields index 0
+    } else {
+      const int e = __ffs(__ballot_sync(FULL, lane < WARPS && w.x == ch && w.y == cl)) - 1;
+      const float4 c = wxyz[pp][e];
+      x1 = c.x, y1 = c.y, z1 = c.z;
+      k = rank_to_k(static_cast<int>(0xFFFFFFFFu - cl), Q, log2bs, N);
+    }
+    if (tid == 0) idx_out[j] = k;
+  }
 }
 
 // Fallback for clouds that do not fit the register-resident kernels: one CTA per scene,
@@ -326,7 +371,6 @@ fps_streaming_kernel(const float *__restrict__ xyz, int ld, long long bstride, i
   xyz += static_cast<long long>(blockIdx.x) * bstride;
   tmp += static_cast<long long>(blockIdx.x) * N;
   idx_out += static_cast<long long>(blockIdx.x) * m;
-  const int bs = 1 << log2bs;
   for (int k = tid; k < N; k += FPS_THREADS) {
     const float *p = xyz + static_cast<long long>(k) * ld;
     const float x = p[0], y = p[1], z = p[2];
@@ -347,20 +391,18 @@ fps_streaming_kernel(const float *__restrict__ xyz, int ld, long long bstride, i
       const float t = fminf(d, tmp[k]);
       tmp[k] = t;
       if (t >= 0.f) {
-        const int tr = k & (bs - 1);
-        const uint32_t trev = log2bs ? (__brev(static_cast<uint32_t>(tr)) >> (32 - log2bs)) : 0u;
         const uint32_t khi = __float_as_uint(t) + 1u;
-        const uint32_t klo = 0xFFFFFFFFu - (trev * static_cast<uint32_t>(Q) + static_cast<uint32_t>(k >> log2bs));
+        const uint32_t klo = 0xFFFFFFFFu - rank_of_k(k, Q, log2bs);
         if (khi > hi || (khi == hi && klo > lo)) { hi = khi; lo = klo; }
       }
     }
-    const uint32_t whi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    const uint32_t wlo = __reduce_max_sync(0xFFFFFFFFu, hi == whi ? lo : 0u);
+    const uint32_t whi = __reduce_max_sync(FULL, hi);
+    const uint32_t wlo = __reduce_max_sync(FULL, hi == whi ? lo : 0u);
     if (lane == 0) wpart[p][warp] = make_uint2(whi, wlo);
     __syncthreads();
     const uint2 w = lane < FPS_WARPS ? wpart[p][lane] : make_uint2(0u, 0u);
-    const uint32_t chi = __reduce_max_sync(0xFFFFFFFFu, w.x);
-    const uint32_t clo = __reduce_max_sync(0xFFFFFFFFu, w.x == chi ? w.y : 0u);
+    const uint32_t chi = __reduce_max_sync(FULL, w.x);
+    const uint32_t clo = __reduce_max_sync(FULL, w.x == chi ? w.y : 0u);
     old = chi == 0u ? 0 : rank_to_k(static_cast<int>(0xFFFFFFFFu - clo), Q, log2bs, N);
     if (tid == 0) idx_out[j] = old;
   }
@@ -375,21 +417,32 @@ int ref_opt_n_threads(int work_size) {
   return v;
 }
 
-template <int CLUSTER, int P, bool ORDERED = false>
+struct RankGeometry {
+  int log2bs, Q;
+  long long R;  // ranks in use
+};
+RankGeometry rank_geometry(int N) {
+  RankGeometry g;
+  const int bs = ref_opt_n_threads(N);
+  g.log2bs = 0;
+  while ((1 << g.log2bs) < bs) ++g.log2bs;
+  g.Q = (N + bs - 1) / bs;
+  g.R = static_cast<long long>(bs) * g.Q;
+  return g;
+}
+
+template <int CLUSTER, int P>
 cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, int N, int m, int log2bs, int Q,
-                            int *idx, cudaStream_t stream, const int *order = nullptr) {
-  auto kern = fps_resident_kernel<CLUSTER, P, ORDERED>;
+                            int *idx, cudaStream_t stream) {
+  auto kern = fps_resident_kernel<CLUSTER, P>;
   const size_t smem = static_cast<size_t>(FPS_THREADS) * P * sizeof(float4);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static bd::PerDeviceOnce configured;  // function attributes are per device
+  const cudaError_t ce = configured.run([&]() {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    if (CLUSTER > 8) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e != cudaSuccess) return e;
-    }
-    configured = true;
-  }
+    if (e == cudaSuccess && CLUSTER > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
+  });
+  if (ce != cudaSuccess) return ce;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B * CLUSTER);
   cfg.blockDim = dim3(FPS_THREADS);
@@ -402,59 +455,55 @@ cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, xyz, ld, bstride, N, m, log2bs, Q, order, idx);
+  return cudaLaunchKernelEx(&cfg, kern, xyz, ld, bstride, N, m, log2bs, Q, idx);
 }
 
 int g_force_cluster = -1;  // test hook: bd_fps_set_cluster()
+int g_bucket_warps = 16;   // tuning hook: bd_fps_grid_set_warps()
 
+constexpr int BUCKET_CAPACITY = 16 * 32 * 4 * 32;  // warps x lanes x slots x points per bucket = 65536 points
 
 }  // namespace
 
 extern "C" int bd_fps_resident_capacity(void) { return 16 * FPS_THREADS * 16; }
+extern "C" int bd_fps_grid_capacity(void) { return BUCKET_CAPACITY; }
+extern "C" long long bd_fps_grid_scratch_bytes(int B, int N) {
+  return static_cast<long long>(B) * ((N + 31) / 32 * 32) * static_cast<long long>(sizeof(float));
+}
 
-// Test / tuning hook: force the cluster size used for large clouds (8 or 16; -1 = automatic).
+// Test / tuning hook: force the cluster size used for large clouds (4, 8 or 16; -1 = automatic).
 extern "C" int bd_fps_set_cluster(int cluster) {
   g_force_cluster = cluster;
   return BD_OK;
 }
-
-extern "C" int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp, int *idx, bd_stream_t stream_);
-
-extern "C" int bd_fps_debug_counters(unsigned long long *out4) {  // host copy of the FPS_DEBUG_COUNT counters
-  BD_CUDA(cudaMemcpyFromSymbol(out4, g_fps_dbg, sizeof(unsigned long long) * 32), "bd_fps_debug_counters");
+// Tuning hook: warps per CTA of the bucket kernel (16 or 32).
+extern "C" int bd_fps_grid_set_warps(int warps) {
+  if (warps != 16 && warps != 32) {
+    bd::set_error("bd_fps_grid_set_warps: 16 or 32");
+    return BD_ERR_INVALID_ARG;
+  }
+  g_bucket_warps = warps;
   return BD_OK;
 }
 
-// bd_fps on spatially ordered points (see fps_resident_kernel): `order` (B, N) is a permutation of
-// 0..N-1 per scene that keeps neighbours together, e.g. bd_grid_order() of the cell list that the
-// ball query of the same level needs anyway.  Same indices as bd_fps, bit for bit.  Clouds outside
-// the 4- / 8-CTA-cluster range fall back to bd_fps.
-extern "C" int bd_fps_ordered(const float *xyz, int ld, int B, int N, int m, const int *order, float *tmp, int *idx,
-                              bd_stream_t stream_) {
-  BD_REQUIRE(xyz && idx && order, "bd_fps_ordered: null pointer");
-  BD_REQUIRE(B > 0 && N > 0 && m >= 0 && ld >= 3, "bd_fps_ordered: bad sizes B=%d N=%d m=%d ld=%d", B, N, m, ld);
+// Furthest point sampling over the cell list of bd_grid_build(xyz, ..., grid_workspace) — same
+// indices as bd_fps, bit for bit.  `scratch`: bd_fps_grid_scratch_bytes(B, N) bytes.
+extern "C" int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *grid_workspace, float *scratch,
+                           int *idx, bd_stream_t stream_) {
+  BD_REQUIRE(xyz && idx && grid_workspace && scratch, "bd_fps_grid: null pointer");
+  BD_REQUIRE(B > 0 && N > 0 && m >= 0 && ld >= 3, "bd_fps_grid: bad sizes B=%d N=%d m=%d ld=%d", B, N, m, ld);
+  BD_REQUIRE(N <= BUCKET_CAPACITY, "bd_fps_grid: N=%d exceeds the capacity of %d points (use bd_fps)", N,
+             BUCKET_CAPACITY);
   if (m == 0) return BD_OK;
-  const int bs = ref_opt_n_threads(N);
-  int log2bs = 0;
-  while ((1 << log2bs) < bs) ++log2bs;
-  const int Q = (N + bs - 1) / bs;
+  const RankGeometry g = rank_geometry(N);
   const long long bstride = static_cast<long long>(N) * ld;
-  const long long T = FPS_THREADS;
+  const float4 *records = bd::grid_sorted_points(grid_workspace, B, N);
   cudaStream_t stream = bd::as_stream(stream_);
-  cudaError_t e;
-  // positions, not ranks, are distributed here: N of them
-  if (N > 4 * T * 13 && N <= 4 * T * 25 && B > 8)
-    e = launch_resident<4, 25, true>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream, order);
-  else if (N > 8 * T * 8 && N <= 8 * T * 13)
-    e = launch_resident<8, 13, true>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream, order);
+  if (g_bucket_warps == 32)
+    fps_bucket_kernel<32, 2, 2><<<B, 1024, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   else
-    return bd_fps(xyz, ld, B, N, m, tmp, idx, stream_);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    bd::set_error("bd_fps_ordered: launch failed: %s", cudaGetErrorString(e));
-    return BD_ERR_CUDA;
-  }
-  BD_CHECK_LAUNCH("bd_fps_ordered");
+    fps_bucket_kernel<16, 4, 4><<<B, 512, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
+  BD_CHECK_LAUNCH("bd_fps_grid");
   return BD_OK;
 }
 
@@ -463,11 +512,9 @@ extern "C" int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp,
   BD_REQUIRE(B > 0 && N > 0 && m >= 0 && ld >= 3, "bd_fps: bad sizes B=%d N=%d m=%d ld=%d", B, N, m, ld);
   if (m == 0) return BD_OK;
   cudaStream_t stream = bd::as_stream(stream_);
-  const int bs = ref_opt_n_threads(N);
-  int log2bs = 0;
-  while ((1 << log2bs) < bs) ++log2bs;
-  const int Q = (N + bs - 1) / bs;
-  const long long R = static_cast<long long>(bs) * Q;  // ranks in use
+  const RankGeometry g = rank_geometry(N);
+  const int log2bs = g.log2bs, Q = g.Q;
+  const long long R = g.R;
   const long long bstride = static_cast<long long>(N) * ld;
   cudaError_t e = cudaSuccess;
   const long long T = FPS_THREADS;
@@ -482,39 +529,34 @@ extern "C" int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp,
     // measured on B200 (50k points): 16-CTA clusters win up to 4 scenes (1.34 vs 1.56 ms); from 8
     // scenes on only ~6 of them are co-resident (one per GPC) and 8-CTA clusters win (1.56 vs 1.92 ms);
     // beyond 8 scenes 4-CTA clusters (25 points per thread) keep up to 37 scenes in a single wave
-    // (2.18 ms for 16-32 scenes vs 3.1-4.6 ms with 8-CTA clusters).
+    // (2.18 ms for 16-32 scenes vs 3.1-4.6 ms with 8-CTA clusters).  Callers that have a cell list
+    // use bd_fps_grid instead (one CTA per scene, a single wave up to 148 scenes).
     int cluster = g_force_cluster > 0 ? g_force_cluster : (B <= 4 ? 16 : (B <= 8 ? 8 : 4));
     if (cluster == 4 && R > 4 * T * 25) cluster = 8;
     if (cluster == 4) {
       e = launch_resident<4, 25>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      if (e != cudaSuccess) {
-        cudaGetLastError();
-        bd::set_error("bd_fps: launch failed: %s", cudaGetErrorString(e));
-        return BD_ERR_CUDA;
+    } else {
+      if (cluster == 16 && R <= 16 * T * 16) {
+        if (R <= 16 * T * 4) e = launch_resident<16, 4>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else if (R <= 16 * T * 7) e = launch_resident<16, 7>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else if (R <= 16 * T * 10) e = launch_resident<16, 10>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else e = launch_resident<16, 16>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        if (e != cudaSuccess && g_force_cluster <= 0) {  // non-portable size refused: retry with 8
+          cudaGetLastError();
+          cluster = 8;
+        }
       }
-      BD_CHECK_LAUNCH("bd_fps");
-      return BD_OK;
-    }
-    if (cluster == 16 && R <= 16 * T * 16) {
-      if (R <= 16 * T * 4) e = launch_resident<16, 4>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else if (R <= 16 * T * 7) e = launch_resident<16, 7>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else if (R <= 16 * T * 10) e = launch_resident<16, 10>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else e = launch_resident<16, 16>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      if (e != cudaSuccess && g_force_cluster <= 0) {  // non-portable size refused: retry with 8
-        cudaGetLastError();
-        cluster = 8;
-      }
-    }
-    if (cluster != 16 || R > 16 * T * 16) {
-      if (R <= 8 * T * 4) e = launch_resident<8, 4>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else if (R <= 8 * T * 8) e = launch_resident<8, 8>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else if (R <= 8 * T * 13) e = launch_resident<8, 13>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else if (R <= 8 * T * 16) e = launch_resident<8, 16>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else if (R <= 16 * T * 16) e = launch_resident<16, 16>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
-      else {
-        BD_REQUIRE(tmp != nullptr, "bd_fps: N=%d exceeds the resident capacity; tmp scratch required", N);
-        fps_streaming_kernel<<<B, FPS_THREADS, 0, stream>>>(xyz, ld, bstride, N, m, log2bs, Q, tmp, idx);
-        e = cudaSuccess;
+      if (cluster != 16 || R > 16 * T * 16) {
+        if (R <= 8 * T * 4) e = launch_resident<8, 4>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else if (R <= 8 * T * 8) e = launch_resident<8, 8>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else if (R <= 8 * T * 13) e = launch_resident<8, 13>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else if (R <= 8 * T * 16) e = launch_resident<8, 16>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else if (R <= 16 * T * 16) e = launch_resident<16, 16>(xyz, ld, bstride, B, N, m, log2bs, Q, idx, stream);
+        else {
+          BD_REQUIRE(tmp != nullptr, "bd_fps: N=%d exceeds the resident capacity; tmp scratch required", N);
+          fps_streaming_kernel<<<B, FPS_THREADS, 0, stream>>>(xyz, ld, bstride, N, m, log2bs, Q, tmp, idx);
+          e = cudaSuccess;
+        }
       }
     }
   }

@@ -579,16 +579,16 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   const size_t tile = static_cast<size_t>(TC_BM) * (NC + 4) * 4;
   const size_t smem = (pipe > tile ? pipe : tile) + 1024;  // slack: the dynamic base is 1024-aligned by hand
   BD_REQUIRE(smem <= 218 * 1024, "bd_linear_tc: tiling needs %zu bytes of shared memory (> 218 KB)", smem);
-  static thread_local bool configured = false;
-  if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
-    BD_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_linear_tc");
-    configured = true;
-  }
+  static bd::PerDeviceOnce configured;  // function attributes are per device
+  BD_CUDA(configured.run([&]() {
+    cudaError_t e = cudaSuccess;
+    const void *kernels[] = {(const void *)linear_tc_kernel<0, 0>, (const void *)linear_tc_kernel<0, 1>,
+                             (const void *)linear_tc_kernel<1, 0>, (const void *)linear_tc_kernel<1, 1>,
+                             (const void *)linear_tc_kernel<0, 2>, (const void *)linear_tc_kernel<2, 0>};
+    for (const void *k : kernels)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    return e;
+  }), "bd_linear_tc");
   const int n_groups = bd::ceil_div(p.N, NC);
   BD_REQUIRE(n_groups <= 65535, "bd_linear_tc: N too large");
   dim3 grid(bd::ceil_div(p.M, TC_BM), n_groups);

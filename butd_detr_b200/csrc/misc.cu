@@ -18,12 +18,14 @@ void set_error(const char *fmt, ...) {
 int g_pdl = 1;
 
 int sm_count() {
-  static thread_local int n = 0;
+  static int cached[64] = {0};  // per device (benign race: every writer stores the same value)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cached[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cached[dev & 63] = n;
   }
   return n;
 }

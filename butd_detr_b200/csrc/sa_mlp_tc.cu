@@ -542,16 +542,13 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
   if (p.K1 <= 16 && N0 == 64 && N1 == 64 && N2 <= 128 && (ns == 32 || ns == 64)) {
     // resident-weights persistent kernel (SA1)
     const size_t smem_r = static_cast<size_t>(parts) * (2 * 64 + N2 + SA_BM) * 128 + 1024;
-    static thread_local bool configured_r = false;
-    static thread_local int n_sm = 0;
-    if (!configured_r) {
-      BD_CUDA(cudaFuncSetAttribute(sa_mlp_resident_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024), "bd_sa_mlp_tc");
-      BD_CUDA(cudaFuncSetAttribute(sa_mlp_resident_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024), "bd_sa_mlp_tc");
-      int dev = 0;
-      BD_CUDA(cudaGetDevice(&dev), "bd_sa_mlp_tc");
-      BD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "bd_sa_mlp_tc");
-      configured_r = true;
-    }
+    static bd::PerDeviceOnce configured_r;  // function attributes are per device
+    BD_CUDA(configured_r.run([&]() {
+      cudaError_t e = cudaFuncSetAttribute(sa_mlp_resident_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(sa_mlp_resident_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      return e;
+    }), "bd_sa_mlp_tc");
+    const int n_sm = bd::sm_count();
     const int tiles = bd::ceil_div(p.M, SA_BM);
     const int per_sm = parts == 1 ? 3 : 2;  // 49 KB of shared memory per CTA in the single-part mode, 97 KB otherwise
     const int ctas = tiles < per_sm * n_sm ? tiles : per_sm * n_sm;
@@ -569,12 +566,12 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
   const size_t tile = static_cast<size_t>(SA_BM) * ((N2 < 128 ? N2 : 128) + 4) * 4;  // pooled in passes of <= 128 columns
   const size_t smem = (pipe > tile ? pipe : tile) + 1024;
   BD_REQUIRE(smem <= 218 * 1024, "bd_sa_mlp_tc: needs %zu bytes of shared memory (> 218 KB)", smem);
-  static thread_local bool configured = false;
-  if (!configured) {
-    BD_CUDA(cudaFuncSetAttribute(sa_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_sa_mlp_tc");
-    BD_CUDA(cudaFuncSetAttribute(sa_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024), "bd_sa_mlp_tc");
-    configured = true;
-  }
+  static bd::PerDeviceOnce configured;  // function attributes are per device
+  BD_CUDA(configured.run([&]() {
+    cudaError_t e = cudaFuncSetAttribute(sa_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sa_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    return e;
+  }), "bd_sa_mlp_tc");
   const dim3 grid(bd::ceil_div(p.M, SA_BM));
   if (parts == 2)
     BD_CUDA(bd::launch_pdl(sa_mlp_tc_kernel<2>, grid, dim3(SA_THREADS), smem, bd::as_stream(stream), p), "bd_sa_mlp_tc");

@@ -29,12 +29,24 @@ SA_CFG = (  # models/backbone_module.py:44-78
     ("sa4", 256, 1.2, 16),
 )
 GRID_BALL_QUERY_MIN_POINTS = 8192
+GRAPH_CACHE_SIZE = 6     # CUDA graphs kept per engine (LRU): each pins the buffers of one input-shape signature
+GRAPH_TOKEN_BUCKET = 16  # text length is padded to a multiple of this before a graph is looked up
+GRID_RULE_K = 200.0  # cell list when nsample >= K * radius^2 (metres): r=.2 -> 8, r=.4 -> 32, r=.8 -> 128
 BN_EPS = 1e-5
 LN_EPS = 1e-5
 
 
 def _round_up(x, m):
     return (x + m - 1) // m * m
+
+
+def grid_ball_query_rule(n, radius, nsample, m):
+    """True when the cell-list ball query (bd_ball_query_grid) should replace the ordered brute-force
+    scan (bd_ball_query) — identical results either way.  Shared by the engine and the
+    `pointnet2._ext` drop-in.  The scan stops at the nsample-th hit, so it wins for big balls /
+    small groups; the cell list tests ~27 cells per centre whatever the cloud size.  Measured on
+    50k-point scenes (profiles/, configs[4]): the cell list wins for r = 0.2 at every nsample."""
+    return n >= GRID_BALL_QUERY_MIN_POINTS and nsample <= 64 and nsample >= GRID_RULE_K * radius * radius
 
 
 # ------------------------------------------------------------------------------ weight packing
@@ -58,9 +70,8 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
-ORDERED_FPS = False  # SA1 FPS over the cell-list order with per-thread pruning (bd_fps_ordered): bit-identical, but
-# measured no faster (1.6 % of threads / 13 % of warps sweep per round, yet one lone sweeping warp still takes ~1000
-# cycles per round, as long as the whole un-pruned sweep with 4 warps per scheduler); kept for the tests and DESIGN.md §4
+FPS_GRID_MIN_BATCH = 1  # scenes from which SA1's FPS runs as the bucketed one-CTA-per-scene kernel over the cell list
+# (bd_fps_grid: a single wave up to 148 scenes) instead of the register-resident cluster kernel (37 scenes per wave)
 DECODER_SPLIT_MIN = 1 << 30  # scenes per half above which the decoder would run as two batch halves on two streams:
 # measured at 32 scenes: 2336 vs 2400 scenes/s — no gain (the kernels of one half already fill a wave), so it is off
 FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
@@ -419,7 +430,7 @@ class ForwardEngine:
             _lib.call("bd_ball_query_grid_query", new_xyz.data_ptr(), xyz.data_ptr(), ld_xyz, B, n, m, float(radius), ns,
                       idx.data_ptr(), grid[0].data_ptr())
             self._grid = None
-        elif n >= GRID_BALL_QUERY_MIN_POINTS:  # cell-list search (identical output, ~100x fewer distance tests)
+        elif grid_ball_query_rule(n, radius, ns, m):  # cell-list search (identical output, ~100x fewer distance tests)
             ws = self._empty(_lib.load().bd_ball_query_grid_workspace_bytes(B, n), dtype=torch.uint8)
             _lib.call("bd_ball_query_grid", new_xyz.data_ptr(), xyz.data_ptr(), ld_xyz, B, n, m, float(radius), ns,
                       idx.data_ptr(), ws.data_ptr())
@@ -519,17 +530,17 @@ class ForwardEngine:
         xyz, ld_xyz, n = pc, ld, N
         feats, ld_feats, C = pc[..., 3:], ld, C_in
         self._grid = None
-        if ORDERED_FPS and N >= GRID_BALL_QUERY_MIN_POINTS:
+        lib = _lib.load()
+        if GRID_BALL_QUERY_MIN_POINTS <= N <= lib.bd_fps_grid_capacity() and B >= FPS_GRID_MIN_BATCH:
             # the cell list of SA1's ball query is built first: its cell order also drives the
-            # pruned furthest-point sampling (bd_fps_ordered)
-            lib = _lib.load()
+            # bucketed furthest-point sampling (bd_fps_grid)
             ws = self._empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8)
             _lib.call("bd_grid_build", pc.data_ptr(), ld, B, N, float(SA_CFG[0][2]), ws.data_ptr())
             self._grid = (ws, N, float(SA_CFG[0][2]))
             inds1 = self._empty(B, SA_CFG[0][1], dtype=torch.int32)
-            tmp = self._empty(B, N) if N > lib.bd_fps_resident_capacity() else None
-            _lib.call("bd_fps_ordered", pc.data_ptr(), ld, B, N, SA_CFG[0][1], lib.bd_grid_order(ws.data_ptr(), B, N),
-                      _lib.ptr(tmp), inds1.data_ptr())
+            scratch = self._empty(lib.bd_fps_grid_scratch_bytes(B, N), dtype=torch.uint8)
+            _lib.call("bd_fps_grid", pc.data_ptr(), ld, B, N, SA_CFG[0][1], ws.data_ptr(), scratch.data_ptr(),
+                      inds1.data_ptr())
         else:
             inds1 = self.fps(pc, ld, B, N, SA_CFG[0][1])
         xyz1 = self.gather_rows(pc, ld, inds1, B, N, SA_CFG[0][1], 3)
@@ -575,13 +586,24 @@ class ForwardEngine:
         """Same result as forward(), replayed from a CUDA graph captured per input-shape
         signature.  Inputs are copied into static buffers; the returned tensors are the graph's
         static outputs and are overwritten by the next call with the same shapes."""
-        keys = [k for k in ("point_clouds", "text_hidden", "text_attention_mask", "det_boxes", "det_bbox_label_mask",
-                            "det_class_ids") if k in inputs]
+        keys = [k for k in ("point_clouds", "seed_features", "seed_xyz", "seed_inds", "text_hidden",
+                            "text_attention_mask", "det_boxes", "det_bbox_label_mask", "det_class_ids") if k in inputs]
+        # the tokenizer pads to the longest utterance of the batch, so L varies from batch to batch:
+        # pad it to a multiple of 16 (padding tokens are masked keys: they contribute exactly nothing)
+        # so that a handful of graphs serves every length; the L-shaped outputs are sliced back
+        L = inputs["text_hidden"].shape[1]
+        Lp = _round_up(L, GRAPH_TOKEN_BUCKET)
+        if Lp != L:
+            inputs = dict(inputs)
+            inputs["text_hidden"] = torch.nn.functional.pad(inputs["text_hidden"], (0, 0, 0, Lp - L))
+            inputs["text_attention_mask"] = torch.nn.functional.pad(inputs["text_attention_mask"], (0, Lp - L))
         sig = tuple((k, tuple(inputs[k].shape), inputs[k].dtype) for k in keys)
         if not hasattr(self, "_graphs"):
-            self._graphs = {}
-        entry = self._graphs.get(sig)
+            self._graphs = {}  # insertion-ordered: least recently used first
+        entry = self._graphs.pop(sig, None)
         if entry is None:
+            while len(self._graphs) >= GRAPH_CACHE_SIZE:  # every graph pins its own pool of intermediates
+                del self._graphs[next(iter(self._graphs))]
             static_in = {k: inputs[k].detach().clone().contiguous() for k in keys}
             with torch.cuda.device(self.device):
                 warm = torch.cuda.Stream()
@@ -595,13 +617,18 @@ class ForwardEngine:
                 with torch.cuda.graph(graph):
                     static_out = self.forward(static_in)
                 entry = (graph, static_in, static_out, _lib.launch_count - n0)
-            self._graphs[sig] = entry
+        self._graphs[sig] = entry  # (re-)inserted last = most recently used
         graph, static_in, static_out, n_launch = entry
         for k in keys:
             static_in[k].copy_(inputs[k], non_blocking=True)
         graph.replay()
         _lib.launch_count += n_launch
-        return dict(static_out)
+        out = dict(static_out)
+        if Lp != L:
+            for k in ("text_feats", "text_attention_mask", "text_memory", "proj_tokens"):
+                if k in out:
+                    out[k] = out[k][:, :L]
+        return out
 
     # ---- whole forward
     @torch.no_grad()
@@ -614,16 +641,23 @@ class ForwardEngine:
         cfg = self.cfg
         ov = overrides or {}
         E = self.d_model
-        pc = inputs["point_clouds"].contiguous().float()
-        _lib.check_cuda(pc)
-        B = pc.shape[0]
+        if "seed_features" in inputs and "seed" not in ov:  # attention-only entry (BASELINE.json configs[3])
+            ov = dict(ov)
+            ov["seed"] = {"features": inputs["seed_features"].transpose(1, 2), "xyz": inputs["seed_xyz"],
+                          "inds": inputs["seed_inds"]}
+        pc = None
+        if "seed" not in ov:
+            pc = inputs["point_clouds"].contiguous().float()
+            _lib.check_cuda(pc)
+        _lib.check_cuda(inputs["text_hidden"])
+        B = inputs["text_hidden"].shape[0]
         ep = {}
         self._live = []
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
-            if "seed" in ov:  # attention-only entry (BASELINE.json configs[3]): backbone output supplied
+            if "seed" in ov:  # backbone output supplied: (B,V,E) token-major features, (B,V,3), (B,V) i32
                 sd = ov["seed"]
-                vis = sd["features"].contiguous().float()  # (B,V,E) token-major
+                vis = sd["features"].contiguous().float()
                 ep["fp2_xyz"], ep["fp2_inds"] = sd["xyz"].contiguous().float(), sd["inds"]
                 ep["fp2_features"] = vis.transpose(1, 2)
             else:

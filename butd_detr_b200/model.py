@@ -78,10 +78,18 @@ class BeaUTyDETR(nn.Module):
         self._attach_text_encoder(text_encoder)
         if input_feature_dim == 3 and pointnet_ckpt is not None:  # bdetr.py:67-70
             self.backbone_net.load_state_dict(torch.load(pointnet_ckpt), strict=False)
-        self.cuda_graph = cuda_graph  # replay the forward from a CUDA graph (static output buffers)
+        # cuda_graph: replay the forward from a CUDA graph.  The returned tensors are then the graph's
+        # static outputs: they are overwritten by the next forward with the same input shapes — clone
+        # what must outlive the next call.
+        self.cuda_graph = cuda_graph
         self._engine = None
         self._engine_key = None
-        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_engine())
+        self._weight_tensors = None
+        # packed / BN-folded weights are derived data: drop them whenever ANY module of the tree loads
+        # a state_dict (the reference loads the backbone alone, bdetr.py:67-70); in-place edits of the
+        # parameters (optimizer steps, EMA) are caught by the version fingerprint in engine()
+        for mod in self.modules():
+            mod.register_load_state_dict_post_hook(self._on_load_state_dict)
 
     # ------------------------------------------------------------------ parameter tree
     def _build_tree(self):
@@ -232,23 +240,42 @@ class BeaUTyDETR(nn.Module):
     def invalidate_engine(self):
         """Drop the packed (BN-folded) weights; they are rebuilt on the next forward."""
         self._engine = None
+        self._weight_tensors = None
+
+    def _on_load_state_dict(self, module, incompatible_keys):
+        self.invalidate_engine()
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self.invalidate_engine()
         return super()._apply(fn, *a, **k)
 
+    def _weights_fingerprint(self):
+        """Device + the sum of the autograd version counters of every tensor the engine packs: any
+        in-place update (optimizer step, EMA, `p.data.copy_`) changes it."""
+        if self._weight_tensors is None:
+            self._weight_tensors = [t for n, t in list(self.named_parameters()) + list(self.named_buffers())
+                                    if not n.startswith("text_encoder.")]
+        return (self.decoder_query_proj.weight.device, sum(t._version for t in self._weight_tensors))
+
     def engine(self):
-        dev = self.decoder_query_proj.weight.device
-        if self._engine is None or self._engine_key != dev:
-            self._engine = ForwardEngine(self.state_dict(), self.cfg, dev)
-            self._engine_key = dev
+        key = self._weights_fingerprint()
+        if self._engine is None or self._engine_key != key:
+            self._engine = ForwardEngine(self.state_dict(), self.cfg, key[0])
+            self._engine_key = key
         return self._engine
 
     # ------------------------------------------------------------------ forward
     def _encode_text(self, inputs, device):
-        """tokenizer -> RoBERTa (bdetr.py:164-171); returns (hidden (B,L,768), HF mask, tokenized)."""
+        """tokenizer -> RoBERTa (bdetr.py:164-171); returns (hidden (B,L,768), HF mask, tokenized).
+        With pre-computed `text_hidden` the `tokenized` entry the loss reads
+        (`tokenized['attention_mask']`, models/losses.py:422,436) is rebuilt from the mask."""
         if "text_hidden" in inputs:
-            return inputs["text_hidden"].to(device), inputs["text_attention_mask"].to(device), None
+            from transformers import BatchEncoding
+            mask = inputs["text_attention_mask"].to(device)
+            tok = {"attention_mask": mask}
+            if "input_ids" in inputs:
+                tok["input_ids"] = inputs["input_ids"].to(device)
+            return inputs["text_hidden"].to(device), mask, BatchEncoding(tok)
         if self.text_encoder is None or self.tokenizer is None:
             raise RuntimeError("no tokenizer/text encoder available: provide inputs['text_hidden'] "
                                "(B,L,768) and inputs['text_attention_mask'] (B,L)")
@@ -259,16 +286,21 @@ class BeaUTyDETR(nn.Module):
 
     def forward(self, inputs, overrides=None):
         """inputs: {point_clouds (B,N,3+C), text: list[str] | (text_hidden, text_attention_mask),
-        det_boxes (B,D,6), det_bbox_label_mask (B,D) bool, det_class_ids (B,D)} -> end_points."""
+        det_boxes (B,D,6), det_bbox_label_mask (B,D) bool, det_class_ids (B,D)} -> end_points.
+        Attention-only entry (BASELINE.json configs[3]): pass `seed_features (B,d_model,V)`,
+        `seed_xyz (B,V,3)` and `seed_inds (B,V) i32` instead of `point_clouds`; the backbone is
+        skipped and the transformer runs on the supplied visual tokens."""
         if self.training:
             raise NotImplementedError(
                 "butd_detr_b200.BeaUTyDETR implements the eval-mode forward (model.eval()); "
                 "the training step (backward, batch-stat BN, dropout) is not built yet")
-        pc = inputs["point_clouds"]
+        pc = inputs["seed_features"] if "seed_features" in inputs else inputs["point_clouds"]
         if not pc.is_cuda:
             raise RuntimeError("CPU not supported: inputs must be CUDA tensors")
         hidden, hf_mask, tokenized = self._encode_text(inputs, pc.device)
-        eng_in = {"point_clouds": pc, "text_hidden": hidden, "text_attention_mask": hf_mask}
+        eng_in = {"text_hidden": hidden, "text_attention_mask": hf_mask}
+        for k in ("seed_features", "seed_xyz", "seed_inds") if "seed_features" in inputs else ("point_clouds",):
+            eng_in[k] = inputs[k]
         if self.butd:
             for k in ("det_boxes", "det_bbox_label_mask", "det_class_ids"):
                 eng_in[k] = inputs[k]

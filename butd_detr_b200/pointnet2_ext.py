@@ -14,7 +14,16 @@ import torch
 from . import _lib
 
 
-GRID_MIN_POINTS = 8192  # clouds at least this large use the cell-list ball query
+GRID_MIN_POINTS = 8192  # clouds at least this large use the cell list (ball query, bucketed FPS)
+FPS_GRID_MIN_BATCH = 1
+
+
+def use_grid_ball_query(n, radius, nsample, m):
+    """One rule for engine.py and this module (DESIGN.md §4, configs[4] sweep): the cell list wins
+    when a ball holds few points compared with the scan the ordered brute force needs to find
+    `nsample` of them, i.e. for large clouds and small balls."""
+    from .engine import grid_ball_query_rule
+    return grid_ball_query_rule(n, radius, nsample, m)
 
 
 def _check(t, name, dtype):
@@ -31,10 +40,18 @@ def furthest_point_sampling(points, nsamples):
     _check(points, "points", torch.float32)
     B, N, _ = points.shape
     out = torch.zeros(B, nsamples, dtype=torch.int32, device=points.device)
-    tmp = None
-    if N > _lib.load().bd_fps_resident_capacity():
-        tmp = torch.empty(B, N, dtype=torch.float32, device=points.device)
+    lib = _lib.load()
     with torch.cuda.device(points.device):
+        if GRID_MIN_POINTS <= N <= lib.bd_fps_grid_capacity() and B >= FPS_GRID_MIN_BATCH:
+            ws = torch.empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8, device=points.device)
+            scratch = torch.empty(lib.bd_fps_grid_scratch_bytes(B, N), dtype=torch.uint8, device=points.device)
+            _lib.call("bd_grid_build", points.data_ptr(), 3, B, N, -1.0, ws.data_ptr())  # cell size picked from the extent
+            _lib.call("bd_fps_grid", points.data_ptr(), 3, B, N, int(nsamples), ws.data_ptr(), scratch.data_ptr(),
+                      out.data_ptr())
+            return out
+        tmp = None
+        if N > lib.bd_fps_resident_capacity():
+            tmp = torch.empty(B, N, dtype=torch.float32, device=points.device)
         _lib.call("bd_fps", points.data_ptr(), 3, B, N, int(nsamples), _lib.ptr(tmp), out.data_ptr())
     return out
 
@@ -72,7 +89,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     with torch.cuda.device(xyz.device):
         # cell-list search (identical output): pays off when the ball holds about nsample points;
         # for small nsample the ordered brute-force scan exits early and wins (measured)
-        if n >= GRID_MIN_POINTS and nsample >= 48:
+        if use_grid_ball_query(n, radius, nsample, m):
             ws = torch.empty(_lib.load().bd_ball_query_grid_workspace_bytes(B, n), dtype=torch.uint8, device=xyz.device)
             _lib.call("bd_ball_query_grid", new_xyz.data_ptr(), xyz.data_ptr(), 3, B, n, m, float(radius),
                       int(nsample), out.data_ptr(), ws.data_ptr())

@@ -54,15 +54,21 @@ const char *bd_arch(void);
  * opt_n_threads(N) threads (cuda_utils.h:20-24). */
 int bd_fps(const float *xyz, int ld, int B, int N, int m, float *tmp, int *idx, bd_stream_t stream);
 int bd_fps_resident_capacity(void);
-/* bd_fps on spatially ordered points: `order` (B,N) is a permutation of 0..N-1 per scene that keeps
- * neighbours together (bd_grid_order of the level's cell list).  A thread's points then sit in a
- * small box and rounds whose new sample is farther away than the box's largest running distance
- * are skipped for that thread.  Same indices as bd_fps, bit for bit. */
-int bd_fps_ordered(const float *xyz, int ld, int B, int N, int m, const int *order, float *tmp,
-                   int *idx, bd_stream_t stream);
-/* Tuning / test hook: force the cluster size (8 or 16 CTAs) used for clouds that need more than
- * one CTA; -1 restores the automatic choice (16 for B <= 8 scenes, else 8). */
+/* Throughput variant of bd_fps over the cell list of the same clouds (bd_grid_build(xyz, ld, B, N,
+ * radius, grid_workspace); any radius, <= 0 picks a cell size): one CTA per scene walks the
+ * cell-ordered points in buckets of 32 and skips every bucket whose bounding box is farther from
+ * the new sample than the bucket's largest running distance (~2 % of the cloud is touched per
+ * round), so a batch of up to 148 scenes runs in one wave.  Same indices as bd_fps, bit for bit.
+ * N <= bd_fps_grid_capacity(); `scratch`: bd_fps_grid_scratch_bytes(B, N) bytes. */
+int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *grid_workspace, float *scratch,
+                int *idx, bd_stream_t stream);
+int bd_fps_grid_capacity(void);
+long long bd_fps_grid_scratch_bytes(int B, int N);
+/* Tuning / test hooks: force the cluster size (4, 8 or 16 CTAs) bd_fps uses for clouds that need
+ * more than one CTA (-1 restores the automatic choice: 16 for B <= 4 scenes, 8 for B <= 8, else 4);
+ * warps per CTA of the bd_fps_grid kernel (16 or 32). */
 int bd_fps_set_cluster(int cluster);
+int bd_fps_grid_set_warps(int warps);
 
 /* gather_points(points (B,C,N), idx (B,m)) -> out (B,C,m)      sampling.cpp:20-43 */
 int bd_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,
@@ -80,16 +86,19 @@ int bd_ball_query(const float *new_xyz, const float *xyz, int ld_xyz, int B, int
                   float radius, int nsample, int *idx, bd_stream_t stream);
 
 /* Same result as bd_ball_query, bit for bit, through a per-scene uniform grid (cell list): points
- * are binned into cells of edge >= radius, each centre visits its 27 neighbour cells and the
- * `nsample` smallest in-ball indices are selected by rank, restoring the reference's index order.
- * Replaces the 102 M brute-force distance tests per scene of ball_query_gpu.cu:14-49 at SA1 by
- * ~0.5 M.  `workspace`: bd_ball_query_grid_workspace_bytes(B, n) bytes of device scratch. */
+ * are binned into cells of edge >= radius, each centre visits its 27 neighbour cells and keeps the
+ * `nsample` smallest in-ball indices (sorted register file + index threshold, no hit cap), which
+ * restores the reference's index order.  Replaces the 102 M brute-force distance tests per scene
+ * of ball_query_gpu.cu:14-49 at SA1 by ~0.5 M.  nsample > 64 falls through to bd_ball_query.
+ * `workspace`: bd_ball_query_grid_workspace_bytes(B, n) bytes of device scratch. */
 long long bd_ball_query_grid_workspace_bytes(int B, int n);
 int bd_ball_query_grid(const float *new_xyz, const float *xyz, int ld_xyz, int B, int n, int m,
                        float radius, int nsample, int *idx, void *workspace, bd_stream_t stream);
 /* The two halves of bd_ball_query_grid: bd_grid_build bins the clouds once (cells of edge >=
- * radius); bd_ball_query_grid_query answers queries against that cell list (same xyz / radius);
- * bd_grid_order returns the device array (B,n) of point indices grouped by cell. */
+ * radius; radius <= 0: 1/32 of the largest extent); bd_ball_query_grid_query answers queries
+ * against that cell list (same xyz; cells >= radius are the efficient case, smaller cells are
+ * visited further out); bd_grid_order returns the device array (B,n) of point indices grouped by
+ * cell.  The same cell list drives bd_fps_grid. */
 int bd_grid_build(const float *xyz, int ld_xyz, int B, int n, float radius, void *workspace,
                   bd_stream_t stream);
 const int *bd_grid_order(void *workspace, int B, int n);

@@ -54,23 +54,71 @@ def test_fps_cluster_sizes_agree(cluster, ext, oracle_lib, cuda_lib):
     assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("kind,B,N,m", [("room", 2, 50000, 2048), ("room", 10, 50000, 1024), ("lattice", 9, 40000, 700),
-                                        ("dup", 3, 50000, 600), ("uniform", 12, 30000, 512)])
-def test_fps_ordered_equals_fps(cuda_lib, oracle_lib, kind, B, N, m):
-    """bd_fps_ordered (cell-list order + per-thread pruning) returns bd_fps's indices bit for bit
-    (8-CTA clusters for B <= 8, 4-CTA clusters beyond; ties, duplicates, partially empty CTAs)."""
+def _fps_grid(cuda_lib, xyz, m, radius, warps=16):
+    """bd_grid_build + bd_fps_grid on a (B,N,3) CUDA tensor."""
     lib = cuda_lib.load()
-    xyz = cloud(11 + B, N, kind, B).cuda()
-    want = torch.zeros(B, m, dtype=torch.int32, device="cuda")
-    cuda_lib.call("bd_fps", xyz.data_ptr(), 3, B, N, m, None, want.data_ptr())
+    B, N, _ = xyz.shape
     ws = torch.empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8, device="cuda")
-    cuda_lib.call("bd_grid_build", xyz.data_ptr(), 3, B, N, 0.2, ws.data_ptr())
-    got = torch.full((B, m), -1, dtype=torch.int32, device="cuda")
-    cuda_lib.call("bd_fps_ordered", xyz.data_ptr(), 3, B, N, m, lib.bd_grid_order(ws.data_ptr(), B, N), None,
-                  got.data_ptr())
+    scratch = torch.empty(lib.bd_fps_grid_scratch_bytes(B, N), dtype=torch.uint8, device="cuda")
+    out = torch.full((B, m), -1, dtype=torch.int32, device="cuda")
+    cuda_lib.call("bd_grid_build", xyz.data_ptr(), 3, B, N, float(radius), ws.data_ptr())
+    lib.bd_fps_grid_set_warps(warps)
+    try:
+        cuda_lib.call("bd_fps_grid", xyz.data_ptr(), 3, B, N, m, ws.data_ptr(), scratch.data_ptr(), out.data_ptr())
+    finally:
+        lib.bd_fps_grid_set_warps(16)
+    return out
+
+
+@pytest.mark.parametrize("kind,B,N,m,radius", [("room", 2, 50000, 2048, 0.2), ("room", 3, 50000, 700, -1.0),
+                                               ("lattice", 9, 40000, 700, 0.2), ("dup", 3, 50000, 600, 0.2),
+                                               ("uniform", 12, 30000, 512, -1.0), ("uniform", 2, 8192, 512, 0.05),
+                                               ("room", 1, 65536, 300, 0.2), ("lattice", 2, 9001, 9001, 0.3),
+                                               ("uniform", 2, 777, 300, -1.0)])
+@pytest.mark.parametrize("warps", [16, 32])
+def test_fps_grid_bit_exact(cuda_lib, oracle_lib, kind, B, N, m, radius, warps):
+    """bd_fps_grid (cell-list order, buckets of 32, bounding-box pruning) returns the oracle's indices bit
+    for bit: ties on lattices, heavy duplication, more samples than distinct points, a partial last
+    bucket, cells of any size (radius <= 0: picked from the extent)."""
+    xyz = cloud(11 + B, N, kind, B)
+    want = oracle_lib.furthest_point_sampling(xyz, m)
+    got = _fps_grid(cuda_lib, xyz.cuda(), m, radius, warps).cpu()
     assert torch.equal(got, want), f"first mismatch at {(got != want).nonzero()[:3].tolist()}"
-    if B <= 2:
-        assert torch.equal(got.cpu(), oracle_lib.furthest_point_sampling(xyz.cpu(), m))
+
+
+@pytest.mark.parametrize("B,m", [(9, 2048), (16, 2048), (37, 1024), (128, 2048)])
+def test_fps_benched_batch_sizes_bit_exact(cuda_lib, oracle_lib, ref_ext, ext, B, m):
+    """The FPS variants the benchmark's batch sizes select — bd_fps with 4-CTA clusters (B > 8) and
+    bd_fps_grid — on B full 50k-point scenes, against the C oracle (every scene) and the reference's
+    own CUDA kernel (sampling_gpu.cu:74-178)."""
+    xyz = cloud(500 + B, 50000, "room", B)
+    want = oracle_lib.furthest_point_sampling(xyz, m)
+    xd = xyz.cuda()
+    got = torch.full((B, m), -1, dtype=torch.int32, device="cuda")
+    cuda_lib.call("bd_fps", xd.data_ptr(), 3, B, 50000, m, None, got.data_ptr())
+    assert torch.equal(got.cpu(), want), "bd_fps (cluster kernel) differs from the oracle"
+    got_grid = _fps_grid(cuda_lib, xd, m, 0.2).cpu()
+    assert torch.equal(got_grid, want), f"bd_fps_grid differs from the oracle at {(got_grid != want).nonzero()[:3].tolist()}"
+    assert torch.equal(ext.furthest_point_sampling(xd, m).cpu(), want), "drop-in furthest_point_sampling differs"
+    if ref_ext is not None:
+        assert torch.equal(ref_ext.furthest_point_sampling(xd, m).cpu(), want), "oracle differs from the reference kernel"
+
+
+def test_fps_grid_skipped_points_and_strided_rows(cuda_lib, oracle_lib):
+    """Points with |p|^2 <= 1e-3 never win (sampling_gpu.cu:105-106); rows of 6 floats (ld = 6)."""
+    from butd_detr_b200 import synth
+    pc = torch.from_numpy(synth.synth_scene(5, 20000, 8)["point_clouds"])[None].clone()
+    pc[0, 100:4000, :3] *= 0.004            # a dense blob inside the skip radius
+    pc[0, 0, :3] = 0.0                      # the start point itself is skipped-class
+    lib = cuda_lib.load()
+    pcd = pc.cuda()
+    ws = torch.empty(lib.bd_ball_query_grid_workspace_bytes(1, 20000), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(lib.bd_fps_grid_scratch_bytes(1, 20000), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(1, 1500, dtype=torch.int32, device="cuda")
+    cuda_lib.call("bd_grid_build", pcd.data_ptr(), 6, 1, 20000, 0.2, ws.data_ptr())
+    cuda_lib.call("bd_fps_grid", pcd.data_ptr(), 6, 1, 20000, 1500, ws.data_ptr(), scratch.data_ptr(), out.data_ptr())
+    want = oracle_lib.furthest_point_sampling(pc[..., :3].contiguous(), 1500)
+    assert torch.equal(out.cpu(), want)
 
 
 def test_fps_strided_input_matches_contiguous(cuda_lib, oracle_lib):
@@ -213,3 +261,51 @@ def test_ball_query_grid_full_scene_sweep(cuda_lib, oracle_lib):
             cuda_lib.call("bd_ball_query_grid", cd.data_ptr(), xd.data_ptr(), 3, 1, 50000, 2048, r, ns, out.data_ptr(),
                           ws.data_ptr())
             assert torch.equal(out.cpu(), oracle_lib.ball_query(new_xyz, xyz, r, ns)), (r, ns)
+
+
+@pytest.mark.parametrize("ns", [1, 7, 16, 33, 64, 65, 100])
+@pytest.mark.parametrize("kind,n,m,r", [("room", 20000, 500, 0.25), ("dup", 9000, 200, 0.9), ("lattice", 12000, 300, 0.5)])
+def test_ball_query_grid_selection_sizes(cuda_lib, oracle_lib, kind, n, m, r, ns):
+    """Register selection of the cell-list query at every group size (1 .. 64: sorted file of 128
+    candidates + index threshold, hundreds to thousands of hits per ball on the dense clouds;
+    > 64 falls through to the ordered scan)."""
+    xyz = cloud(61, n, kind, 2)
+    new_xyz = (xyz[:, :m] + 0.01).contiguous()
+    want = oracle_lib.ball_query(new_xyz, xyz, r, ns)
+    out = torch.full((2, m, ns), -1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(cuda_lib.load().bd_ball_query_grid_workspace_bytes(2, n), dtype=torch.uint8, device="cuda")
+    xd, cd = xyz.cuda(), new_xyz.cuda()
+    cuda_lib.call("bd_ball_query_grid", cd.data_ptr(), xd.data_ptr(), 3, 2, n, m, float(r), ns, out.data_ptr(), ws.data_ptr())
+    assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("build_radius", [-1.0, 0.07, 0.5])
+def test_ball_query_on_a_grid_of_another_cell_size(cuda_lib, oracle_lib, build_radius):
+    """bd_ball_query_grid_query on a cell list built for a different radius (cells smaller than the
+    ball: more cells are visited; larger: fewer) — identical indices."""
+    xyz = cloud(62, 15000, "room", 2)
+    new_xyz = xyz[:, :400].contiguous()
+    xd, cd = xyz.cuda(), new_xyz.cuda()
+    ws = torch.empty(cuda_lib.load().bd_ball_query_grid_workspace_bytes(2, 15000), dtype=torch.uint8, device="cuda")
+    cuda_lib.call("bd_grid_build", xd.data_ptr(), 3, 2, 15000, build_radius, ws.data_ptr())
+    for r, ns in ((0.2, 64), (0.35, 16)):
+        out = torch.full((2, 400, ns), -1, dtype=torch.int32, device="cuda")
+        cuda_lib.call("bd_ball_query_grid_query", cd.data_ptr(), xd.data_ptr(), 3, 2, 15000, 400, r, ns, out.data_ptr(),
+                      ws.data_ptr())
+        assert torch.equal(out.cpu(), oracle_lib.ball_query(new_xyz, xyz, r, ns)), (build_radius, r, ns)
+
+
+def test_grid_build_survives_non_finite_points(cuda_lib, oracle_lib):
+    """A NaN / inf coordinate must not hang the cell-list build (it used to loop forever doubling the
+    cell size); the finite points are still binned and queried."""
+    xyz = cloud(63, 9000, "uniform", 1)
+    xyz[0, 5] = float("inf")
+    xyz[0, 6, 1] = float("nan")
+    xd = xyz.cuda()
+    cd = xyz[:, 100:164].contiguous().cuda()
+    ws = torch.empty(cuda_lib.load().bd_ball_query_grid_workspace_bytes(1, 9000), dtype=torch.uint8, device="cuda")
+    out = torch.full((1, 64, 16), -1, dtype=torch.int32, device="cuda")
+    cuda_lib.call("bd_ball_query_grid", cd.data_ptr(), xd.data_ptr(), 3, 1, 9000, 64, 0.3, 16, out.data_ptr(), ws.data_ptr())
+    torch.cuda.synchronize()
+    # non-finite points are never inside a ball (NaN / inf distances), exactly as in the ordered scan
+    assert torch.equal(out.cpu(), oracle_lib.ball_query(xyz[:, 100:164].contiguous(), xyz, 0.3, 16))

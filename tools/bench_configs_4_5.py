@@ -25,14 +25,15 @@ def bench(fn, n=20, warm=3):
     return e0.elapsed_time(e1) / n
 
 
+PARTS = sys.argv[1:] or ["3", "4"]
 print("## configs[3] — attention-only path (256 box tokens, 80 text tokens, 1024 seeds, 256 queries, 3 enc + 6 dec)\n")
 print("| batch | precision | ms/step | scenes/s |\n|---|---|---|---|")
-for prec in ("bf16x3", "fp32"):
+for prec in (("fp16", "bf16x3", "fp32") if "3" in PARTS else ()):
     model = BeaUTyDETR(text_encoder=None, precision=prec)
     synth.fill_state_dict_(model.state_dict(), 0)
     model = model.cuda().eval()
     eng = model.engine()
-    for B in (1, 8, 32):
+    for B in (1, 8, 32, 128):
         inp = {k: v.cuda() for k, v in synth.synth_batch(5, B, 2048, 80, 256).items()}
         g = torch.Generator(device="cuda").manual_seed(B)
         seed = {"features": torch.randn(B, 1024, 288, device="cuda", generator=g),
@@ -49,8 +50,9 @@ for prec in ("bf16x3", "fp32"):
 
 print("\n## configs[4] — ball-query sweep, N = 50 000 points, m = 2 048 FPS centres (idx only)\n")
 print("algorithmic bytes = B (12 N + 12 m + 4 m nsample); peak = %.1f GB/s (measured)\n" % PEAK)
-print("| B | radius | nsample | ordered scan us | GB/s | frac | cell list us | GB/s | frac | identical |\n|---|---|---|---|---|---|---|---|---|---|")
-for B in (1, 8, 64):
+print("| B | radius | nsample | ordered scan us | GB/s | frac | cell list us (build + query) | query only us | GB/s | frac | identical | rule picks |\n|---|---|---|---|---|---|---|---|---|---|---|---|")
+from butd_detr_b200.engine import grid_ball_query_rule
+for B in ((1, 8, 64, 128) if "4" in PARTS else ()):
     pcs = torch.from_numpy(np.stack([synth.synth_scene(50 + b)["point_clouds"] for b in range(B)])).cuda()
     inds = torch.zeros(B, 2048, dtype=torch.int32, device="cuda")
     _lib.call("bd_fps", pcs.data_ptr(), 6, B, 50000, 2048, None, inds.data_ptr())
@@ -63,5 +65,7 @@ for B in (1, 8, 64):
             o2 = torch.zeros_like(o1)
             t1 = bench(lambda: _lib.call("bd_ball_query", cen.data_ptr(), pcs.data_ptr(), 6, B, 50000, 2048, r, ns, o1.data_ptr()), 5, 1) * 1e3
             t2 = bench(lambda: _lib.call("bd_ball_query_grid", cen.data_ptr(), pcs.data_ptr(), 6, B, 50000, 2048, r, ns, o2.data_ptr(), ws.data_ptr()), 5, 1) * 1e3
+            t3 = bench(lambda: _lib.call("bd_ball_query_grid_query", cen.data_ptr(), pcs.data_ptr(), 6, B, 50000, 2048, r, ns, o2.data_ptr(), ws.data_ptr()), 5, 1) * 1e3
             by = B * (12 * 50000 + 12 * 2048 + 4 * 2048 * ns)
-            print(f"| {B} | {r} | {ns} | {t1:.1f} | {by / t1 / 1e3:.1f} | {by / t1 / 1e3 / PEAK:.5f} | {t2:.1f} | {by / t2 / 1e3:.1f} | {by / t2 / 1e3 / PEAK:.5f} | {torch.equal(o1, o2)} |")
+            pick = "cell list" if grid_ball_query_rule(50000, r, ns, 2048) else "scan"
+            print(f"| {B} | {r} | {ns} | {t1:.1f} | {by / t1 / 1e3:.1f} | {by / t1 / 1e3 / PEAK:.5f} | {t2:.1f} | {t3:.1f} | {by / t2 / 1e3:.1f} | {by / t2 / 1e3 / PEAK:.5f} | {torch.equal(o1, o2)} | {pick} |", flush=True)
