@@ -221,16 +221,41 @@ fps_resident_kernel(const float *__restrict__ xyz, int ld, long long bstride, in
 //   adjacent) buckets go to different warps, so the few active buckets of a round spread over the CTA.
 //   `tmin` (B, 32 * ceil(N / 32)) floats: running distances in record order (global scratch; a
 //   bucket's entries are only ever touched by the lanes of its own warp, so no fences are needed).
-// Per round: every lane tests its SLOTS buckets against the new sample (registers only) -> ballot ->
-// the warp visits its active buckets, up to U at a time (loads in flight together): 20 bytes per
-// point from L2, new minima written back only where they changed, 2x REDUX for the bucket's new
-// farthest point -> lane-level maximum over the slots -> 2x REDUX -> ONE CTA barrier -> 2x REDUX.
-template <int WARPS, int SLOTS, int U>
+// One round (measured latencies, tools/ubench/latency.cu: REDUX 35, REDUX pair 70, L2 load ~380 cycles):
+//   every lane tests its SLOTS buckets against the new sample (registers) -> SLOTS ballots -> the warp
+//   lists its active buckets, up to U at a time, and issues their loads together (20 bytes per point
+//   from L2) -> new minima (written back only where they changed) -> each lane's candidate = the best
+//   of its FRESH points and of its cached buckets that were not touched -> one REDUX pair -> the
+//   warp's winner posts (key, xyz) to shared memory and the warp arrives on an mbarrier -> only then
+//   the bookkeeping the next rounds need (per visited bucket: REDUX pair + 3 shuffles for its new
+//   farthest point) -> wait on the mbarrier -> REDUX pair over the WARPS posts.
+// The indices are written as raw keys and converted (an integer division) after the last round.
+__device__ unsigned long long g_fps_stats[16];  // STATS variant: [0] bucket visits, [1] visit batches, [2] warp-rounds with a visit, [3] warp-rounds; [8..14] cycles of warp 0 of CTA 0 per phase
+#define FPS_T(i) do { if (STATS && blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } } while (0)
+
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+template <int WARPS, int SLOTS, int U, bool STATS = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ xyz, int ld, long long bstride, int N,
                   int m, int log2bs, int Q, float *__restrict__ tmin, int *__restrict__ idx_out) {
   __shared__ uint2 wkey[2][WARPS];
   __shared__ float4 wxyz[2][WARPS];
+  __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int scene = blockIdx.x;
   const int nb = (N + 31) >> 5;
@@ -238,6 +263,10 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
   float *tm = tmin + static_cast<long long>(scene) * nb * 32;
   xyz += static_cast<long long>(scene) * bstride;
   idx_out += static_cast<long long>(scene) * m;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   float bx0[SLOTS], by0[SLOTS], bz0[SLOTS], bx1[SLOTS], by1[SLOTS], bz1[SLOTS];  // bucket bounding boxes
   float cx[SLOTS], cy[SLOTS], cz[SLOTS];                                         // farthest point of the bucket
@@ -278,13 +307,20 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
   }
   const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
   float x1 = x0, y1 = y0, z1 = z0;
-  if (tid == 0) idx_out[0] = 0;
+  if (tid == 0) idx_out[0] = -1;  // raw keys; converted after the loop (entry 0 is always index 0)
+  __syncthreads();               // mbarrier initialised
 
+  long long tacc[7] = {0, 0, 0, 0, 0, 0, 0}, tprev = STATS ? clock64() : 0;
   for (int j = 1; j < m; ++j) {
     const int pp = j & 1;
+    // ---- which of my buckets can change?
+    bool act[SLOTS];
+    unsigned am[SLOTS];
+    uint32_t ch = 0u, cl = 0u;  // lane candidate (key) and its coordinates
+    float ccx = 0.f, ccy = 0.f, ccz = 0.f;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-      bool active = false;
+      act[s] = false;
       if (hi[s] != 0u) {
         // lower bound of the distance from the sample to the bucket's box, by the kernel's own
         // distance expression (rounding is monotonic, so it never exceeds a member's distance; the
@@ -293,71 +329,134 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
         const float ex = fmaxf(fmaxf(bx0[s] - x1, x1 - bx1[s]), 0.f), ey = fmaxf(fmaxf(by0[s] - y1, y1 - by1[s]), 0.f),
                     ez = fmaxf(fmaxf(bz0[s] - z1, z1 - bz1[s]), 0.f);
         const float lb = fmaf(ez, ez, fmaf(ex, ex, ey * ey));
-        active = !(lb * 0.99999f > best);
+        act[s] = !(lb * 0.99999f > best);
       }
-      unsigned mask = __ballot_sync(FULL, active);
-      while (mask) {
-        int o[U];
-        float4 p[U];
+      am[s] = __ballot_sync(FULL, act[s]);
+      // a bucket that is not visited keeps its cached farthest point: it competes as it is
+      if (!act[s] && (hi[s] > ch || (hi[s] == ch && lo[s] > cl))) ch = hi[s], cl = lo[s], ccx = cx[s], ccy = cy[s], ccz = cz[s];
+    }
+    FPS_T(0);
+    unsigned st_visits = 0, st_batches = 0;
+    if (STATS) {
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) st_visits += __popc(am[s]);
+    }
+    // ---- visit the active buckets, U at a time; the last batch's bookkeeping waits until the warp has posted
+    int ls[U], ol[U];
+    ls[0] = -1;
+    float4 p[U];
+    float t[U];
+    uint32_t h[U];
+    bool posted = false;
+    while (true) {
+      bool left = false;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) left = left || am[s] != 0u;
+      if (!left && posted) break;
+      if (left) {
+        if (STATS) ++st_batches;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          ls[u] = -1, ol[u] = 0;
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            if (ls[u] < 0 && am[s] != 0u) {
+              ls[u] = s, ol[u] = __ffs(am[s]) - 1;
+              am[s] &= am[s] - 1u;
+            }
+          }
+        }
         float told[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          o[u] = mask ? __ffs(mask) - 1 : -1;
-          mask &= mask - 1u;
+          const int i = ls[u] < 0 ? -1 : (((ls[u] * 32 + ol[u]) * WARPS + warp) << 5) + lane;
+          p[u] = (i >= 0 && i < N) ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+          told[u] = i >= 0 ? tm[i] : -2.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (o[u] < 0) continue;
-          const int i = (((s * 32 + o[u]) * WARPS + warp) << 5) + lane;
-          p[u] = i < N ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-          told[u] = tm[i];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (o[u] < 0) continue;
-          const int i = (((s * 32 + o[u]) * WARPS + warp) << 5) + lane;
+          const int i = ls[u] < 0 ? -1 : (((ls[u] * 32 + ol[u]) * WARPS + warp) << 5) + lane;
           const float d = bd::sqdist_ref(p[u].x, p[u].y, p[u].z, x1, y1, z1);
-          const float t = fminf(d, told[u]);
-          if (t < told[u]) tm[i] = t;
-          const uint32_t h = dist_key(t);
-          const uint32_t wh = __reduce_max_sync(FULL, h);
-          const uint32_t l = (h == wh && wh != 0u) ? 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs) : 0u;
-          const uint32_t wl = __reduce_max_sync(FULL, l);
-          const int src = __ffs(__ballot_sync(FULL, h == wh && l == wl)) - 1;
-          const float wx = __shfl_sync(FULL, p[u].x, src), wy = __shfl_sync(FULL, p[u].y, src),
-                      wz = __shfl_sync(FULL, p[u].z, src);
-          if (lane == o[u]) hi[s] = wh, lo[s] = wl, cx[s] = wx, cy[s] = wy, cz[s] = wz;
+          t[u] = fminf(d, told[u]);
+          if (t[u] < told[u]) tm[i] = t[u];  // told = -2 for the lanes without a point: never true
+          h[u] = dist_key(t[u]);
+          if (h[u] >= ch && h[u] != 0u) {
+            const uint32_t l = 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs);
+            if (h[u] > ch || l > cl) ch = h[u], cl = l, ccx = p[u].x, ccy = p[u].y, ccz = p[u].z;
+          }
         }
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) left = s == 0 ? am[0] != 0u : (left || am[s] != 0u);
+      }
+      if (left) FPS_T(1); else FPS_T(2);
+      if (!left && !posted) {
+        // ---- every bucket of the warp is accounted for: post the warp's winner, arrive
+        const uint32_t wh = __reduce_max_sync(FULL, ch);
+        const uint32_t wl = __reduce_max_sync(FULL, ch == wh ? cl : 0u);
+        const int src = __ffs(__ballot_sync(FULL, ch == wh && (cl == wl || wh == 0u))) - 1;
+        if (lane == src) {
+          wkey[pp][warp] = make_uint2(wh, wl);
+          wxyz[pp][warp] = make_float4(ccx, ccy, ccz, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(smem_u32(&bar));
+        posted = true;
+        FPS_T(3);
+      }
+      // ---- bookkeeping of the batch just visited: the bucket's new farthest point
+      if (ls[0] >= 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ls[u] < 0) continue;
+          const uint32_t bh = __reduce_max_sync(FULL, h[u]);
+          const uint32_t l = (h[u] == bh && bh != 0u) ? 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs) : 0u;
+          const uint32_t bl = __reduce_max_sync(FULL, l);
+          const int bsrc = __ffs(__ballot_sync(FULL, h[u] == bh && l == bl)) - 1;
+          const float wx = __shfl_sync(FULL, p[u].x, bsrc), wy = __shfl_sync(FULL, p[u].y, bsrc),
+                      wz = __shfl_sync(FULL, p[u].z, bsrc);
+          // (one-hot slot mask rather than `ls[u] == s`: the compiler turns the latter into indexed
+          //  stores, which would move the five state arrays to local memory)
+          const unsigned sel = lane == ol[u] ? 1u << ls[u] : 0u;
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            const bool upd = (sel >> s) & 1u;
+            hi[s] = upd ? bh : hi[s], lo[s] = upd ? bl : lo[s];
+            cx[s] = upd ? wx : cx[s], cy[s] = upd ? wy : cy[s], cz[s] = upd ? wz : cz[s];
+          }
+        }
+        ls[0] = -1;  // done
+        FPS_T(4);
       }
     }
-    // farthest point over the lane's buckets, the warp, the CTA
-    uint32_t mh = hi[0], ml = lo[0];
-    float mx = cx[0], my = cy[0], mz = cz[0];
-#pragma unroll
-    for (int s = 1; s < SLOTS; ++s) {
-      if (hi[s] > mh || (hi[s] == mh && lo[s] > ml)) mh = hi[s], ml = lo[s], mx = cx[s], my = cy[s], mz = cz[s];
+    if (STATS && lane == 0) {
+      atomicAdd(&g_fps_stats[0], st_visits);
+      atomicAdd(&g_fps_stats[1], st_batches);
+      atomicAdd(&g_fps_stats[2], st_visits ? 1ull : 0ull);
+      atomicAdd(&g_fps_stats[3], 1ull);
     }
-    const uint32_t wh = __reduce_max_sync(FULL, mh);
-    const uint32_t wl = __reduce_max_sync(FULL, mh == wh ? ml : 0u);
-    const int src = __ffs(__ballot_sync(FULL, mh == wh && (ml == wl || wh == 0u))) - 1;
-    if (lane == src) {
-      wkey[pp][warp] = make_uint2(wh, wl);
-      wxyz[pp][warp] = make_float4(mx, my, mz, 0.f);
-    }
-    __syncthreads();
+    // ---- all warps have posted: the CTA's winner is the next sample
+    mbar_wait_cta(smem_u32(&bar), static_cast<uint32_t>(j - 1) & 1u);
+    FPS_T(5);
     const uint2 w = lane < WARPS ? wkey[pp][lane] : make_uint2(0u, 0u);
-    const uint32_t ch = __reduce_max_sync(FULL, w.x);
-    const uint32_t cl = __reduce_max_sync(FULL, w.x == ch ? w.y : 0u);
-    int k;
-    if (ch == 0u) {
-      x1 = x0, y1 = y0, z1 = z0, k = 0;  // nothing selectable: reference yields index 0
+    const uint32_t gh = __reduce_max_sync(FULL, w.x);
+    const uint32_t gl = __reduce_max_sync(FULL, w.x == gh ? w.y : 0u);
+    if (gh == 0u) {
+      x1 = x0, y1 = y0, z1 = z0;  // nothing selectable: reference yields index 0
     } else {
-      const int e = __ffs(__ballot_sync(FULL, lane < WARPS && w.x == ch && w.y == cl)) - 1;
+      const int e = __ffs(__ballot_sync(FULL, lane < WARPS && w.x == gh && w.y == gl)) - 1;
       const float4 c = wxyz[pp][e];
       x1 = c.x, y1 = c.y, z1 = c.z;
-      k = rank_to_k(static_cast<int>(0xFFFFFFFFu - cl), Q, log2bs, N);
     }
-    if (tid == 0) idx_out[j] = k;
+    if (tid == 0) idx_out[j] = gh == 0u ? -1 : static_cast<int>(0xFFFFFFFFu - gl);  // raw rank
+    FPS_T(6);
+  }
+  if (STATS && blockIdx.x == 0 && tid == 0) {
+    for (int i = 0; i < 7; ++i) g_fps_stats[8 + i] = static_cast<unsigned long long>(tacc[i]);
+  }
+  __syncthreads();
+  for (int j = tid; j < m; j += WARPS * 32) {
+    const int r = idx_out[j];
+    idx_out[j] = r < 0 ? 0 : rank_to_k(r, Q, log2bs, N);
   }
 }
 
@@ -459,7 +558,8 @@ cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, 
 }
 
 int g_force_cluster = -1;  // test hook: bd_fps_set_cluster()
-int g_bucket_warps = 16;   // tuning hook: bd_fps_grid_set_warps()
+int g_bucket_warps = 32;   // tuning hook: bd_fps_grid_set_warps(); measured: 4.07 / 4.67 ms (32 warps) vs 4.64 / 5.35 ms (16) at 1 / 128 scenes
+int g_bucket_stats = 0;    // tools: bd_fps_grid_stats()
 
 constexpr int BUCKET_CAPACITY = 16 * 32 * 4 * 32;  // warps x lanes x slots x points per bucket = 65536 points
 
@@ -486,6 +586,18 @@ extern "C" int bd_fps_grid_set_warps(int warps) {
   return BD_OK;
 }
 
+// Tools: enable (1) / disable (0) the counting variant of the bucket kernel and read its counters
+// (out8: bucket visits, visit batches, warp-rounds with a visit, warp-rounds; NULL = only switch).
+extern "C" int bd_fps_grid_stats(int enable, unsigned long long *out8) {
+  g_bucket_stats = enable;
+  if (out8) {
+    BD_CUDA(cudaMemcpyFromSymbol(out8, g_fps_stats, sizeof(unsigned long long) * 16), "bd_fps_grid_stats");
+    unsigned long long zero[16] = {0};
+    BD_CUDA(cudaMemcpyToSymbol(g_fps_stats, zero, sizeof(zero)), "bd_fps_grid_stats");
+  }
+  return BD_OK;
+}
+
 // Furthest point sampling over the cell list of bd_grid_build(xyz, ..., grid_workspace) — same
 // indices as bd_fps, bit for bit.  `scratch`: bd_fps_grid_scratch_bytes(B, N) bytes.
 extern "C" int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *grid_workspace, float *scratch,
@@ -499,7 +611,9 @@ extern "C" int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *
   const long long bstride = static_cast<long long>(N) * ld;
   const float4 *records = bd::grid_sorted_points(grid_workspace, B, N);
   cudaStream_t stream = bd::as_stream(stream_);
-  if (g_bucket_warps == 32)
+  if (g_bucket_stats)
+    fps_bucket_kernel<16, 4, 4, true><<<B, 512, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
+  else if (g_bucket_warps == 32)
     fps_bucket_kernel<32, 2, 2><<<B, 1024, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   else
     fps_bucket_kernel<16, 4, 4><<<B, 512, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);

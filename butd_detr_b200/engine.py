@@ -70,8 +70,9 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
-FPS_GRID_MIN_BATCH = 1  # scenes from which SA1's FPS runs as the bucketed one-CTA-per-scene kernel over the cell list
-# (bd_fps_grid: a single wave up to 148 scenes) instead of the register-resident cluster kernel (37 scenes per wave)
+FPS_GRID_MIN_BATCH = 48  # scenes from which SA1's FPS runs as the bucketed one-CTA-per-scene kernel over the cell list
+# (bd_fps_grid: a single wave up to 148 scenes, ~4.3 ms whatever the batch) instead of the register-resident cluster
+# kernel (37 scenes per wave of 2.18 ms: 4.36 ms at 64 scenes, 8.72 ms at 128)
 DECODER_SPLIT_MIN = 1 << 30  # scenes per half above which the decoder would run as two batch halves on two streams:
 # measured at 32 scenes: 2336 vs 2400 scenes/s — no gain (the kernels of one half already fill a wave), so it is off
 FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
@@ -281,9 +282,11 @@ class ForwardEngine:
             out = self._empty(M, N)
         assert out.stride(1) == 1
         lda2 = 0 if add is None else add.stride(0)
-        tc_ok = ((N >= 16 or M >= 1024) and K % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and
+        # the choice of kernel must not depend on the batch size (a batch has to equal its scenes run
+        # alone, bit for bit): only K and alignment decide
+        tc_ok = (K % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and
                  (add is None or (add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0)))
-        if self.precision != "fp32" and tc_ok:  # tensor cores (narrow heads padded to 16 columns when M is large); K = 3 / 6 inputs stay fp32
+        if self.precision != "fp32" and tc_ok:  # tensor cores (narrow heads padded to 16 columns); K = 3 / 6 inputs stay fp32
             wide, bn = lin_tiling(M, N)
             if add is not None and self.split == 3:
                 wide = False  # two raw fp32 chunks (x and pos) + hi/lo weights of a 288-wide tile: no room for 2 stages

@@ -69,6 +69,9 @@ long long bd_fps_grid_scratch_bytes(int B, int N);
  * warps per CTA of the bd_fps_grid kernel (16 or 32). */
 int bd_fps_set_cluster(int cluster);
 int bd_fps_grid_set_warps(int warps);
+/* Tools: switch the counting variant of the bd_fps_grid kernel on / off and read (and clear) its
+ * counters: out16 = {bucket visits, visit batches, warp-rounds with a visit, warp-rounds, -, -, -, -, 7 per-phase cycle sums of warp 0 of CTA 0, -}. */
+int bd_fps_grid_stats(int enable, unsigned long long *out16);
 
 /* gather_points(points (B,C,N), idx (B,m)) -> out (B,C,m)      sampling.cpp:20-43 */
 int bd_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,
