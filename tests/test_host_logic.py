@@ -61,5 +61,8 @@ def test_bench_work_figures():
     assert bound == "tensor" and abs(flops - 2 * 2048 * 64 * (6 * 64 + 64 * 64 + 64 * 128)) < 1
     assert abs(flops / 1e9 - 3.32) < 0.02
     assert bench.algorithmic_work("bd_fps", [0, 6, 4, 50000, 2048]) == ("hbm", 4 * (12 * 50000 + 4 * 2048))
-    assert set(bench.PARITY_GATE) == set(bench.PARITY_MEASURED) == {"fp32", "fp16", "bf16x3"}
-    assert all(bench.PARITY_MEASURED[k] < bench.PARITY_GATE[k] for k in bench.PARITY_GATE)
+    assert bench.algorithmic_work("bd_fps_grid", [0, 6, 4, 50000, 2048]) == ("hbm", 4 * (12 * 50000 + 4 * 2048))
+    assert bench.PARITY_GATE == {"fp32": 1e-3, "bf16x3": 1e-3, "fp16": 1e-2}  # north_star's tolerances
+    assert not hasattr(bench, "PARITY_MEASURED")  # the error is measured in every run (bench.measure_parity)
+    att = bench.attention_summary(4000.0, [])
+    assert abs(att["attention_gemm_flop_roofline_frac"] - 4000 * 17.9e9 / (bench.tensor_peak() * 1e12)) < 1e-12
