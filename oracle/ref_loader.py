@@ -1,5 +1,8 @@
 """TEST INFRASTRUCTURE — imports the UNMODIFIED reference Python from /root/reference (exists
-only in the build container) so golden vectors can be generated from the reference itself.
+only in the build container) or from its git-ignored copy `baseline/_ref/` (made by
+baseline/install_ref.py; travels to the GPU box) so golden vectors can be generated from the
+reference itself and the reference's own consumers / modules can be run on this package's
+outputs and operators.
 
 The reference cannot be constructed offline as-is: it needs RoBERTa weights
 from the hub, `ipdb`/`termcolor`, a `pointnet2._ext` extension that only has CUDA kernels,
@@ -18,7 +21,8 @@ import types
 
 import torch
 
-REF = "/root/reference"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference" if os.path.isdir("/root/reference/models") else os.path.join(_ROOT, "baseline", "_ref")
 
 
 def available():
@@ -64,13 +68,25 @@ def _cwd(path):
 _models = None
 
 
-def import_reference():
-    """Returns the reference's `models` package (BeaUTyDETR, ...)."""
+def import_reference(ext=None):
+    """Returns the reference's `models` package (BeaUTyDETR, ...).  `ext`: the module served as
+    `pointnet2._ext` — the CPU oracle by default, `butd_detr_b200.pointnet2_ext` to run the
+    reference's PointNet++ modules on the CUDA drop-in."""
     global _models
     if _models is not None:
+        if ext is not None:
+            import pointnet2
+            sys.modules["pointnet2._ext"] = ext
+            pointnet2._ext = ext
+            for name in ("pointnet2_utils", "pointnet2.pointnet2_utils"):
+                if name in sys.modules:
+                    sys.modules[name]._ext = ext
         return _models
-    assert available(), "/root/reference is not present on this machine"
-    from . import point_ops
+    assert available(), "neither /root/reference nor baseline/_ref is present on this machine"
+    if ext is None:
+        from . import point_ops
+    else:
+        point_ops = ext
     for name in ("ipdb", "termcolor"):
         if name not in sys.modules:
             m = types.ModuleType(name)
@@ -92,9 +108,9 @@ def import_reference():
     return models
 
 
-def build_reference_model(**kwargs):
+def build_reference_model(ext=None, **kwargs):
     """`BeaUTyDETR(**kwargs)` from the reference, eval mode, fake text front-end."""
-    models = import_reference()
+    models = import_reference(ext)
     with _cwd(REF):
         model = models.BeaUTyDETR(**kwargs)
     return model.eval()
