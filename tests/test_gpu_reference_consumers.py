@@ -50,6 +50,10 @@ def pair(ref):
     """(our model, reference model with the same weights, device inputs, our end_points, reference end_points)."""
     from butd_detr_b200 import BeaUTyDETR, pointnet2_ext, synth
     ref_loader, _ = ref
+    # the reference layers must compute in fp32 like the reference's pinned torch 1.10 did for matmuls;
+    # cuDNN's TF32 convolutions (on by default) would cost it 1e-3
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     ours = BeaUTyDETR(num_queries=CFG["num_queries"], num_decoder_layers=CFG["dec"], text_encoder=None)
     sd = synth.fill_state_dict_(ours.state_dict(), 0)
     ours = ours.cuda().eval()
