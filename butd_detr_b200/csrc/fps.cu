@@ -249,36 +249,66 @@ __device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
-template <int WARPS, int SLOTS, int U, bool STATS = false>
+constexpr int BK_MAX_BUCKETS = 2048;  // 65536 points
+constexpr int BK_U = 2;               // buckets a warp has in flight together (a round lists ~29: two per warp)
+
+// shared-memory image of the bucket kernel (dynamic): the mutable half of the bucket state — any warp
+// may visit any bucket — the per-round work list and the posts of the warps
+// (a warp OWNS a contiguous run of `per` = ceil(nb / WARPS) buckets — a compact slab of the scene — and the
+//  state of bucket b sits at (b / per) * 32 * SLOTS + b % per: the 32 owner lanes read consecutive words)
+struct BucketSmem {
+  float best[BK_MAX_BUCKETS];        // largest running distance in the bucket (-1: nothing selectable)
+  uint32_t lo[BK_MAX_BUCKETS];       // ~rank of the point that holds it
+  float cx[BK_MAX_BUCKETS], cy[BK_MAX_BUCKETS], cz[BK_MAX_BUCKETS];  // ... and its coordinates
+  unsigned short list[2][BK_MAX_BUCKETS];  // active buckets of the round
+  unsigned count[2];
+  uint2 wkey[2][32];
+  float4 wxyz[2][32];
+  unsigned long long bar;
+};
+
+// One round (measured: REDUX pair 70, L2 load ~380-500 cycles; ncu: the first version of this kernel
+// spent a third of its time waiting for the warp that happened to own most of the round's active
+// buckets — hence the CTA-wide work list):
+//   owner lanes test their SLOTS buckets against the new sample (box in registers, largest distance
+//   from shared memory) and append the active ones to the round's list -> CTA barrier -> the warps
+//   take the listed buckets round-robin, BK_U at a time (loads in flight together: 20 bytes per point
+//   from L2; new minima written back only where they changed), fold their points into the lane
+//   candidates and store the bucket's new farthest point (REDUX pair + one lane's stores) -> lane
+//   candidates also cover the lane's untouched buckets -> REDUX pair -> post, arrive / wait on an
+//   mbarrier -> REDUX pair over the posts.  Indices are written as raw keys and converted (an integer
+//   division) after the last round.
+template <int WARPS, int SLOTS, bool STATS = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ xyz, int ld, long long bstride, int N,
                   int m, int log2bs, int Q, float *__restrict__ tmin, int *__restrict__ idx_out) {
-  __shared__ uint2 wkey[2][WARPS];
-  __shared__ float4 wxyz[2][WARPS];
-  __shared__ __align__(8) unsigned long long bar;
+  extern __shared__ __align__(16) unsigned char bk_smem[];
+  BucketSmem &S = *reinterpret_cast<BucketSmem *>(bk_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int scene = blockIdx.x;
   const int nb = (N + 31) >> 5;
+  const int per = (nb + WARPS - 1) / WARPS;  // buckets owned by a warp (<= 32 * SLOTS)
   const float4 *pts = records + static_cast<long long>(scene) * N;
   float *tm = tmin + static_cast<long long>(scene) * nb * 32;
   xyz += static_cast<long long>(scene) * bstride;
   idx_out += static_cast<long long>(scene) * m;
   if (tid == 0) {
-    mbar_init(smem_u32(&bar), WARPS);
+    mbar_init(smem_u32(&S.bar), WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    S.count[0] = S.count[1] = 0u;
   }
+  for (int b = tid; b < BK_MAX_BUCKETS; b += WARPS * 32) S.best[b] = -1.0f, S.lo[b] = 0u, S.cx[b] = S.cy[b] = S.cz[b] = 0.f;
+  __syncthreads();
 
-  float bx0[SLOTS], by0[SLOTS], bz0[SLOTS], bx1[SLOTS], by1[SLOTS], bz1[SLOTS];  // bucket bounding boxes
-  float cx[SLOTS], cy[SLOTS], cz[SLOTS];                                         // farthest point of the bucket
-  uint32_t hi[SLOTS], lo[SLOTS];                                                 // ... and its key
+  // owner side (SLOTS buckets per lane): bounding box as centre + half extent, inflated by 1e-5 so that
+  // the rounding of centre / extent never shrinks it
+  float bcx[SLOTS], bcy[SLOTS], bcz[SLOTS], bhx[SLOTS], bhy[SLOTS], bhz[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    bx0[s] = by0[s] = bz0[s] = bx1[s] = by1[s] = bz1[s] = 0.f;
-    cx[s] = cy[s] = cz[s] = 0.f;
-    hi[s] = lo[s] = 0u;
+    bcx[s] = bcy[s] = bcz[s] = bhx[s] = bhy[s] = bhz[s] = 0.f;
     for (int o = 0; o < 32; ++o) {
-      const int b = (s * 32 + o) * WARPS + warp;
-      if (b >= nb) break;  // warp-uniform
+      const int b = warp * per + s * 32 + o;
+      if (s * 32 + o >= per || b >= nb) break;  // warp-uniform
       const int i = (b << 5) + lane;
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
       bool valid = i < N;
@@ -299,152 +329,173 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
         }
       }
       const bool any = __any_sync(FULL, valid);
-      if (lane == o) {
-        bx0[s] = mn[0], by0[s] = mn[1], bz0[s] = mn[2], bx1[s] = mx[0], by1[s] = mx[1], bz1[s] = mx[2];
-        hi[s] = any ? dist_key(1e10f) : 0u;  // every selectable point starts at 1e10: active in round 1
+      if (lane == o && any) {
+        bcx[s] = 0.5f * (mn[0] + mx[0]), bcy[s] = 0.5f * (mn[1] + mx[1]), bcz[s] = 0.5f * (mn[2] + mx[2]);
+        bhx[s] = 0.5f * (mx[0] - mn[0]) + 1e-5f, bhy[s] = 0.5f * (mx[1] - mn[1]) + 1e-5f, bhz[s] = 0.5f * (mx[2] - mn[2]) + 1e-5f;
+        S.best[warp * (32 * SLOTS) + s * 32 + o] = 1e10f;  // every selectable point starts at 1e10: active in round 1
       }
     }
   }
+  // the warp's slab: bounding box of all its buckets; while the sample is farther from it than the slab's
+  // largest running distance, none of the warp's buckets can change and the warp's winner is the cached one
+  float sbx, sby, sbz, shx, shy, shz;
+  {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if (S.best[warp * (32 * SLOTS) + s * 32 + lane] >= 0.f) {
+        mn[0] = fminf(mn[0], bcx[s] - bhx[s]), mx[0] = fmaxf(mx[0], bcx[s] + bhx[s]);
+        mn[1] = fminf(mn[1], bcy[s] - bhy[s]), mx[1] = fmaxf(mx[1], bcy[s] + bhy[s]);
+        mn[2] = fminf(mn[2], bcz[s] - bhz[s]), mx[2] = fmaxf(mx[2], bcz[s] + bhz[s]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        mn[c] = fminf(mn[c], __shfl_xor_sync(FULL, mn[c], off));
+        mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL, mx[c], off));
+      }
+    }
+    sbx = 0.5f * (mn[0] + mx[0]), sby = 0.5f * (mn[1] + mx[1]), sbz = 0.5f * (mn[2] + mx[2]);
+    shx = 0.5f * (mx[0] - mn[0]) + 1e-5f, shy = 0.5f * (mx[1] - mn[1]) + 1e-5f, shz = 0.5f * (mx[2] - mn[2]) + 1e-5f;
+  }
+  float slab_best = 1e10f;   // upper bound of the running distances in the slab (-1: nothing selectable)
+  bool slab_dirty = true;    // a bucket of the slab was visited since the cached winner was computed
+  uint32_t own_h = 0u, own_l = 0u;  // cached winner over the warp's own buckets (uniform), coordinates
+  float own_x = 0.f, own_y = 0.f, own_z = 0.f;
   const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
   float x1 = x0, y1 = y0, z1 = z0;
   if (tid == 0) idx_out[0] = -1;  // raw keys; converted after the loop (entry 0 is always index 0)
-  __syncthreads();               // mbarrier initialised
+  __syncthreads();
 
   long long tacc[7] = {0, 0, 0, 0, 0, 0, 0}, tprev = STATS ? clock64() : 0;
   for (int j = 1; j < m; ++j) {
     const int pp = j & 1;
-    // ---- which of my buckets can change?
-    bool act[SLOTS];
-    unsigned am[SLOTS];
-    uint32_t ch = 0u, cl = 0u;  // lane candidate (key) and its coordinates
+    // ---- owner lanes: which of my buckets can change?  Those go on the round's list; the others compete
+    //      with their cached farthest point.  Skipped altogether while the sample is far from the slab.
+    float cb = -1.0f;  // lane candidate: distance, key, coordinates
+    uint32_t cl = 0u;
     float ccx = 0.f, ccy = 0.f, ccz = 0.f;
+    bool slab_far;
+    {
+      const float ex = fmaxf(fabsf(x1 - sbx) - shx, 0.f), ey = fmaxf(fabsf(y1 - sby) - shy, 0.f),
+                  ez = fmaxf(fabsf(z1 - sbz) - shz, 0.f);
+      slab_far = fmaf(ez, ez, fmaf(ex, ex, ey * ey)) * 0.99999f > slab_best;
+    }
+    if (slab_far && !slab_dirty) {  // warp-uniform
+      if (lane == 0 && own_h != 0u) cb = __uint_as_float(own_h - 1u), cl = own_l, ccx = own_x, ccy = own_y, ccz = own_z;
+    } else {
+      int cbk = -1;  // the lane's candidate is the cached farthest point of bucket state cbk
+      unsigned am[SLOTS];
+      int total = 0;
+      float lane_max = -1.0f;
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      act[s] = false;
-      if (hi[s] != 0u) {
-        // lower bound of the distance from the sample to the bucket's box, by the kernel's own
-        // distance expression (rounding is monotonic, so it never exceeds a member's distance; the
-        // factor leaves a margin anyway)
-        const float best = __uint_as_float(hi[s] - 1u);
-        const float ex = fmaxf(fmaxf(bx0[s] - x1, x1 - bx1[s]), 0.f), ey = fmaxf(fmaxf(by0[s] - y1, y1 - by1[s]), 0.f),
-                    ez = fmaxf(fmaxf(bz0[s] - z1, z1 - bz1[s]), 0.f);
+      for (int s = 0; s < SLOTS; ++s) {
+        const int b = warp * (32 * SLOTS) + s * 32 + lane;  // state index (conflict-free)
+        const float bf = S.best[b];
+        lane_max = fmaxf(lane_max, bf);
+        // lower bound of the distance from the sample to the bucket's box, by the kernel's own distance
+        // expression (rounding is monotonic; the box is inflated and the factor leaves a margin)
+        const float ex = fmaxf(fabsf(x1 - bcx[s]) - bhx[s], 0.f), ey = fmaxf(fabsf(y1 - bcy[s]) - bhy[s], 0.f),
+                    ez = fmaxf(fabsf(z1 - bcz[s]) - bhz[s], 0.f);
         const float lb = fmaf(ez, ez, fmaf(ex, ex, ey * ey));
-        act[s] = !(lb * 0.99999f > best);
+        const bool act = !(lb * 0.99999f > bf);  // bf = -1 (nothing selectable): never active
+        am[s] = __ballot_sync(FULL, act);
+        total += __popc(am[s]);
+        if (!act && bf >= cb && bf >= 0.f) {
+          const uint32_t l = S.lo[b];
+          if (bf > cb || l > cl) cb = bf, cl = l, cbk = b;
+        }
       }
-      am[s] = __ballot_sync(FULL, act[s]);
-      // a bucket that is not visited keeps its cached farthest point: it competes as it is
-      if (!act[s] && (hi[s] > ch || (hi[s] == ch && lo[s] > cl))) ch = hi[s], cl = lo[s], ccx = cx[s], ccy = cy[s], ccz = cz[s];
+      if (total) {  // warp-uniform
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&S.count[pp], static_cast<unsigned>(total));
+        base = __shfl_sync(FULL, base, 0);
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          if ((am[s] >> lane) & 1u) S.list[pp][base + __popc(am[s] & ((1u << lane) - 1u))] = static_cast<unsigned short>(warp * (32 * SLOTS) + s * 32 + lane);  // state index
+          base += __popc(am[s]);
+        }
+      }
+      if (cbk >= 0) ccx = S.cx[cbk], ccy = S.cy[cbk], ccz = S.cz[cbk];
+      // refresh the slab's cached winner (over the buckets that are NOT being visited) and bound
+      const uint32_t ch = dist_key(cb);
+      own_h = __reduce_max_sync(FULL, ch);
+      own_l = __reduce_max_sync(FULL, ch == own_h ? cl : 0u);
+      const int src = __ffs(__ballot_sync(FULL, ch == own_h && (cl == own_l || own_h == 0u))) - 1;
+      own_x = __shfl_sync(FULL, ccx, src), own_y = __shfl_sync(FULL, ccy, src), own_z = __shfl_sync(FULL, ccz, src);
+      slab_best = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(lane_max, 0.f))));  // >= 0: bits order = value order
+      if (__all_sync(FULL, lane_max < 0.f)) slab_best = -1.0f;
+      slab_dirty = total != 0;  // visited buckets are missing from the cached winner: recompute next round
     }
+    if (tid == 0) S.count[pp ^ 1] = 0u;  // last read before the previous round's posts
     FPS_T(0);
-    unsigned st_visits = 0, st_batches = 0;
-    if (STATS) {
+    __syncthreads();
+    FPS_T(1);
+    // ---- the listed buckets, round-robin over the warps
+    const int n = static_cast<int>(S.count[pp]);
+    if (STATS && tid == 0) atomicAdd(&g_fps_stats[0], static_cast<unsigned long long>(n));
+    for (int e0 = warp; e0 < n; e0 += BK_U * WARPS) {
+      int bk[BK_U], si[BK_U];
+      float4 p[BK_U];
+      float told[BK_U];
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) st_visits += __popc(am[s]);
-    }
-    // ---- visit the active buckets, U at a time; the last batch's bookkeeping waits until the warp has posted
-    int ls[U], ol[U];
-    ls[0] = -1;
-    float4 p[U];
-    float t[U];
-    uint32_t h[U];
-    bool posted = false;
-    while (true) {
-      bool left = false;
-#pragma unroll
-      for (int s = 0; s < SLOTS; ++s) left = left || am[s] != 0u;
-      if (!left && posted) break;
-      if (left) {
-        if (STATS) ++st_batches;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          ls[u] = -1, ol[u] = 0;
-#pragma unroll
-          for (int s = 0; s < SLOTS; ++s) {
-            if (ls[u] < 0 && am[s] != 0u) {
-              ls[u] = s, ol[u] = __ffs(am[s]) - 1;
-              am[s] &= am[s] - 1u;
-            }
-          }
-        }
-        float told[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = ls[u] < 0 ? -1 : (((ls[u] * 32 + ol[u]) * WARPS + warp) << 5) + lane;
-          p[u] = (i >= 0 && i < N) ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-          told[u] = i >= 0 ? tm[i] : -2.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = ls[u] < 0 ? -1 : (((ls[u] * 32 + ol[u]) * WARPS + warp) << 5) + lane;
-          const float d = bd::sqdist_ref(p[u].x, p[u].y, p[u].z, x1, y1, z1);
-          t[u] = fminf(d, told[u]);
-          if (t[u] < told[u]) tm[i] = t[u];  // told = -2 for the lanes without a point: never true
-          h[u] = dist_key(t[u]);
-          if (h[u] >= ch && h[u] != 0u) {
-            const uint32_t l = 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs);
-            if (h[u] > ch || l > cl) ch = h[u], cl = l, ccx = p[u].x, ccy = p[u].y, ccz = p[u].z;
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) left = s == 0 ? am[0] != 0u : (left || am[s] != 0u);
+      for (int u = 0; u < BK_U; ++u) {
+        const int e = e0 + u * WARPS;
+        si[u] = e < n ? static_cast<int>(S.list[pp][e]) : -1;                          // state index
+        bk[u] = e < n ? (si[u] / (32 * SLOTS)) * per + si[u] % (32 * SLOTS) : -1;     // bucket id (record order)
+        const int i = (bk[u] << 5) + lane;
+        p[u] = (bk[u] >= 0 && i < N) ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        told[u] = bk[u] >= 0 ? tm[i] : -2.0f;
       }
-      if (left) FPS_T(1); else FPS_T(2);
-      if (!left && !posted) {
-        // ---- every bucket of the warp is accounted for: post the warp's winner, arrive
-        const uint32_t wh = __reduce_max_sync(FULL, ch);
-        const uint32_t wl = __reduce_max_sync(FULL, ch == wh ? cl : 0u);
-        const int src = __ffs(__ballot_sync(FULL, ch == wh && (cl == wl || wh == 0u))) - 1;
-        if (lane == src) {
-          wkey[pp][warp] = make_uint2(wh, wl);
-          wxyz[pp][warp] = make_float4(ccx, ccy, ccz, 0.f);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cta(smem_u32(&bar));
-        posted = true;
-        FPS_T(3);
-      }
-      // ---- bookkeeping of the batch just visited: the bucket's new farthest point
-      if (ls[0] >= 0) {
+      if (STATS && lane == 0) atomicAdd(&g_fps_stats[1], 1ull);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (ls[u] < 0) continue;
-          const uint32_t bh = __reduce_max_sync(FULL, h[u]);
-          const uint32_t l = (h[u] == bh && bh != 0u) ? 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs) : 0u;
-          const uint32_t bl = __reduce_max_sync(FULL, l);
-          const int bsrc = __ffs(__ballot_sync(FULL, h[u] == bh && l == bl)) - 1;
-          const float wx = __shfl_sync(FULL, p[u].x, bsrc), wy = __shfl_sync(FULL, p[u].y, bsrc),
-                      wz = __shfl_sync(FULL, p[u].z, bsrc);
-          // (one-hot slot mask rather than `ls[u] == s`: the compiler turns the latter into indexed
-          //  stores, which would move the five state arrays to local memory)
-          const unsigned sel = lane == ol[u] ? 1u << ls[u] : 0u;
-#pragma unroll
-          for (int s = 0; s < SLOTS; ++s) {
-            const bool upd = (sel >> s) & 1u;
-            hi[s] = upd ? bh : hi[s], lo[s] = upd ? bl : lo[s];
-            cx[s] = upd ? wx : cx[s], cy[s] = upd ? wy : cy[s], cz[s] = upd ? wz : cz[s];
-          }
+      for (int u = 0; u < BK_U; ++u) {
+        if (bk[u] < 0) continue;  // warp-uniform
+        const int i = (bk[u] << 5) + lane;
+        const float d = bd::sqdist_ref(p[u].x, p[u].y, p[u].z, x1, y1, z1);
+        const float t = fminf(d, told[u]);
+        if (t < told[u]) tm[i] = t;
+        const uint32_t r = 0xFFFFFFFFu - rank_of_k(__float_as_int(p[u].w), Q, log2bs);  // padding lanes: t = -2, never compete
+        if (t > cb || (t == cb && r > cl)) cb = t, cl = r, ccx = p[u].x, ccy = p[u].y, ccz = p[u].z;
+        // the bucket's new farthest point (its owner tests against it from the next round on)
+        const uint32_t h = dist_key(t);
+        const uint32_t bh = __reduce_max_sync(FULL, h);
+        const uint32_t l = (h == bh && bh != 0u) ? r : 0u;
+        const uint32_t bl = __reduce_max_sync(FULL, l);
+        if (h == bh && l == bl && (bh != 0u || lane == 0)) {  // one lane (ranks are unique)
+          S.best[si[u]] = bh ? t : -1.0f, S.lo[si[u]] = bl;
+          S.cx[si[u]] = p[u].x, S.cy[si[u]] = p[u].y, S.cz[si[u]] = p[u].z;
         }
-        ls[0] = -1;  // done
-        FPS_T(4);
       }
     }
-    if (STATS && lane == 0) {
-      atomicAdd(&g_fps_stats[0], st_visits);
-      atomicAdd(&g_fps_stats[1], st_batches);
-      atomicAdd(&g_fps_stats[2], st_visits ? 1ull : 0ull);
-      atomicAdd(&g_fps_stats[3], 1ull);
+    FPS_T(2);
+    // ---- post the warp's winner, arrive
+    {
+      const uint32_t ch = dist_key(cb);
+      const uint32_t wh = __reduce_max_sync(FULL, ch);
+      const uint32_t wl = __reduce_max_sync(FULL, ch == wh ? cl : 0u);
+      const int src = __ffs(__ballot_sync(FULL, ch == wh && (cl == wl || wh == 0u))) - 1;
+      if (lane == src) {
+        S.wkey[pp][warp] = make_uint2(wh, wl);
+        S.wxyz[pp][warp] = make_float4(ccx, ccy, ccz, 0.f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(smem_u32(&S.bar));
     }
+    FPS_T(3);
     // ---- all warps have posted: the CTA's winner is the next sample
-    mbar_wait_cta(smem_u32(&bar), static_cast<uint32_t>(j - 1) & 1u);
+    mbar_wait_cta(smem_u32(&S.bar), static_cast<uint32_t>(j - 1) & 1u);
     FPS_T(5);
-    const uint2 w = lane < WARPS ? wkey[pp][lane] : make_uint2(0u, 0u);
+    const uint2 w = lane < WARPS ? S.wkey[pp][lane] : make_uint2(0u, 0u);
     const uint32_t gh = __reduce_max_sync(FULL, w.x);
     const uint32_t gl = __reduce_max_sync(FULL, w.x == gh ? w.y : 0u);
     if (gh == 0u) {
       x1 = x0, y1 = y0, z1 = z0;  // nothing selectable: reference yields index 0
     } else {
       const int e = __ffs(__ballot_sync(FULL, lane < WARPS && w.x == gh && w.y == gl)) - 1;
-      const float4 c = wxyz[pp][e];
+      const float4 c = S.wxyz[pp][e];
       x1 = c.x, y1 = c.y, z1 = c.z;
     }
     if (tid == 0) idx_out[j] = gh == 0u ? -1 : static_cast<int>(0xFFFFFFFFu - gl);  // raw rank
@@ -558,7 +609,7 @@ cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, 
 }
 
 int g_force_cluster = -1;  // test hook: bd_fps_set_cluster()
-int g_bucket_warps = 32;   // tuning hook: bd_fps_grid_set_warps(); measured: 4.07 / 4.67 ms (32 warps) vs 4.64 / 5.35 ms (16) at 1 / 128 scenes
+int g_bucket_warps = 16;   // tuning hook: bd_fps_grid_set_warps(); measured: 3.39 / 3.95 ms (16 warps) vs 4.00 / 4.48 ms (32) at 1 / 128 scenes
 int g_bucket_stats = 0;    // tools: bd_fps_grid_stats()
 
 constexpr int BUCKET_CAPACITY = 16 * 32 * 4 * 32;  // warps x lanes x slots x points per bucket = 65536 points
@@ -611,12 +662,19 @@ extern "C" int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *
   const long long bstride = static_cast<long long>(N) * ld;
   const float4 *records = bd::grid_sorted_points(grid_workspace, B, N);
   cudaStream_t stream = bd::as_stream(stream_);
+  static bd::PerDeviceOnce configured;  // function attributes are per device
+  BD_CUDA(configured.run([&]() {
+    cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_bucket_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_bucket_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
+    return e;
+  }), "bd_fps_grid");
   if (g_bucket_stats)
-    fps_bucket_kernel<16, 4, 4, true><<<B, 512, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
+    fps_bucket_kernel<16, 4, true><<<B, 512, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   else if (g_bucket_warps == 32)
-    fps_bucket_kernel<32, 2, 2><<<B, 1024, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
+    fps_bucket_kernel<32, 2><<<B, 1024, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   else
-    fps_bucket_kernel<16, 4, 4><<<B, 512, 0, stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
+    fps_bucket_kernel<16, 4><<<B, 512, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   BD_CHECK_LAUNCH("bd_fps_grid");
   return BD_OK;
 }

@@ -15,7 +15,7 @@ from . import _lib
 
 
 GRID_MIN_POINTS = 8192  # clouds at least this large use the cell list (ball query, bucketed FPS)
-FPS_GRID_MIN_BATCH = 48  # as engine.FPS_GRID_MIN_BATCH (measured cross-over with the cluster kernel)
+FPS_GRID_MIN_BATCH = 38  # as engine.FPS_GRID_MIN_BATCH (measured cross-over with the cluster kernel)
 
 
 def use_grid_ball_query(n, radius, nsample, m):

@@ -66,7 +66,7 @@ def _fps_grid(cuda_lib, xyz, m, radius, warps=16):
     try:
         cuda_lib.call("bd_fps_grid", xyz.data_ptr(), 3, B, N, m, ws.data_ptr(), scratch.data_ptr(), out.data_ptr())
     finally:
-        lib.bd_fps_grid_set_warps(32)
+        lib.bd_fps_grid_set_warps(16)
     return out
 
 

@@ -41,7 +41,7 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 4, 8, 16, 32, 64, 128, 148]:
         b.zero_()
         ts.append(bench(lambda: _lib.call("bd_fps_grid", pcs.data_ptr(), 6, B, N, m, ws.data_ptr(), scratch.data_ptr(), b.data_ptr())))
         same = same and bool(torch.equal(a, b))
-    lib.bd_fps_grid_set_warps(32)
+    lib.bd_fps_grid_set_warps(16)
     print(f"| {B} | {t0:.3f} | {tb:.3f} | {ts[0]:.3f} | {ts[1]:.3f} | {same} |", flush=True)
 
 # pruning statistics of the bucket kernel (counting variant)
@@ -58,11 +58,10 @@ lib.bd_fps_grid_stats(1, ctypes.cast(cnt, ctypes.c_void_p))
 _lib.call("bd_fps_grid", pcs.data_ptr(), 6, B, N, m, ws.data_ptr(), scratch.data_ptr(), out.data_ptr())
 torch.cuda.synchronize()
 lib.bd_fps_grid_stats(0, ctypes.cast(cnt, ctypes.c_void_p))
-v, bt, wr, wt = cnt[0], cnt[1], cnt[2], cnt[3]
+v, bt = cnt[0], cnt[1]
 nb = (N + 31) // 32
 print(f"bucket visits per scene-round: {v / B / (m - 1):.1f} of {nb} buckets ({100 * v / B / (m - 1) / nb:.2f} %), "
-      f"equivalent full sweeps per scene: {v / B / nb:.1f}; visit batches per warp-round: {bt / wt:.2f}; "
-      f"warp-rounds with a visit: {100 * wr / wt:.1f} %")
+      f"equivalent full sweeps per scene: {v / B / nb:.1f}; visit batches per warp-round: {bt / B / 16 / (m - 1):.2f}")
 ph = [cnt[8 + i] / (m - 1) for i in range(7)]
-print("warp 0 of scene 0, cycles per round: tests+ballots %.0f | visit batches (more left) %.0f | last batch / no visit %.0f | "
-      "post+arrive %.0f | bookkeeping %.0f | mbarrier wait %.0f | CTA reduce %.0f | total %.0f" % (*ph, sum(ph)))
+print("warp 0 of scene 0, cycles per round: tests+append %.0f | list barrier %.0f | visits %.0f | post+arrive %.0f | "
+      "mbarrier wait %.0f | CTA reduce %.0f | total %.0f" % (ph[0], ph[1], ph[2], ph[3], ph[5], ph[6], sum(ph)))
