@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbutd_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DFPS_DEBUG_COUNT=" + os.environ["FPS_DEBUG_COUNT"]] if os.environ.get("FPS_DEBUG_COUNT") else []) + (["-DSA1_NO_POOL"] if os.environ.get("SA1_NO_POOL") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+FLAGS = (["-DBD_ATTN_EXPERIMENTS"] if os.environ.get("BD_ATTN_EXPERIMENTS") else []) + (["-DSA1_NO_POOL"] if os.environ.get("SA1_NO_POOL") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 

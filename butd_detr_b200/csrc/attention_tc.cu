@@ -652,9 +652,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
 // warp-specialised kernel above (default), 0 = the first-generation single-role kernel.
 static int g_attn_impl = 1, g_attn_dbg = 0;
 extern "C" int bd_attention_tc_select(int impl) {
-  BD_REQUIRE((impl & 15) == 0 || (impl & 15) == 1, "bd_attention_tc_select: impl must be 0 or 1");
+  BD_REQUIRE(impl >= 0 && ((impl & 15) == 0 || (impl & 15) == 1), "bd_attention_tc_select: impl must be 0 or 1");
   g_attn_impl = impl & 15;
-  g_attn_dbg = impl >> 4;  // undocumented: timing experiments (results are garbage when non-zero)
+#ifdef BD_ATTN_EXPERIMENTS  // tools/attn_experiments.py: bits 4.. switch the softmax / the two MMAs off (timing only, garbage results)
+  g_attn_dbg = impl >> 4;
+#else
+  BD_REQUIRE((impl >> 4) == 0, "bd_attention_tc_select: the timing-experiment bits need a -DBD_ATTN_EXPERIMENTS build");
+#endif
   return BD_OK;
 }
 

@@ -196,7 +196,9 @@ __device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4 &hi, uin
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  // .satfinite: magnitudes beyond fp16's 65504 saturate instead of becoming inf (an inf operand would
+  // turn the whole accumulator row into inf / NaN); NaN stays NaN.  Same instruction count (F2FP.SATFINITE).
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 // 8 fp32 -> operand chunk(s): parts == 2: bf16 hi + bf16 lo; parts == 1: fp16 (lo untouched)

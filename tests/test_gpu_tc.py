@@ -211,3 +211,48 @@ def test_launch_policies_do_not_change_results(cuda_lib):
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
     assert torch.isfinite(outs[0]).all()
+
+
+def test_fp16_operands_saturate_instead_of_overflowing(cuda_lib):
+    """fp16 operand mode: activations / weights beyond 65504 saturate (cvt.rn.satfinite) — the result
+    stays finite and equals the product of the clamped operands; NaN inputs still propagate."""
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(77)
+    M, N, K = 256, 64, 64
+    A = torch.randn(M, K, device="cuda", generator=g)
+    A[3, 5], A[100, 0], A[200, 63] = 3.0e5, -7.0e4, 65504.0
+    W = torch.randn(N, K, device="cuda", generator=g) / 8
+    W[7, 5] = 1.0e6
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 1)
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    cuda_lib.call("bd_linear_tc", A.data_ptr(), K, None, 0, Wp.data_ptr(), None, Y.data_ptr(), N, M, N, K, KC, nch, BN, nsub, 0, 1)
+    assert bool(torch.isfinite(Y).all())
+    want = (A.clamp(-65504, 65504).half().double() @ W.clamp(-65504, 65504).half().double().t()).float()
+    torch.testing.assert_close(Y, want, rtol=1e-4, atol=1e-2)
+    A[9, 9] = float("nan")
+    cuda_lib.call("bd_linear_tc", A.data_ptr(), K, None, 0, Wp.data_ptr(), None, Y.data_ptr(), N, M, N, K, KC, nch, BN, nsub, 0, 1)
+    assert bool(torch.isnan(Y[9]).all()) and bool(torch.isfinite(Y[8]).all())
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16"])
+def test_unfused_sa_level_path_matches_fused(cuda_lib, precision):
+    """engine.FUSED_SA = False routes the set-abstraction levels through bd_group_rows / bd_sa_group_linear_tc
+    -> bd_linear_tc -> bd_linear_pool_tc instead of the one-kernel bd_sa_mlp_tc: same features."""
+    from butd_detr_b200 import BeaUTyDETR, engine, synth
+    model = BeaUTyDETR(num_queries=32, num_decoder_layers=1, num_encoder_layers=1, text_encoder=None, precision=precision)
+    synth.fill_state_dict_(model.state_dict(), 0)
+    model = model.cuda().eval()
+    inputs = {k: v.cuda() for k, v in synth.synth_batch(23, 2, 4096, 16, 32).items()}
+    fused = {k: v.clone() for k, v in model(inputs).items() if torch.is_tensor(v)}
+    engine.FUSED_SA = False
+    try:
+        model.invalidate_engine()
+        unfused = model(inputs)
+    finally:
+        engine.FUSED_SA = True
+        model.invalidate_engine()
+    tol = 2e-3 if precision == "bf16x3" else 3e-2  # fp2_features are O(10); hidden activations are re-rounded between kernels
+    for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+        torch.testing.assert_close(unfused[k], fused[k], rtol=tol, atol=tol)
+    for k in ("sa1_inds", "sa2_inds"):
+        assert torch.equal(unfused[k], fused[k])

@@ -1,0 +1,36 @@
+"""Target of the compute-sanitizer runs (profiles/r02_sanitizer_*.log): one configs[0]-sized forward, eager and
+CUDA-graph replay, plus the cell-list kernels (grid build, bucketed FPS, ball query) on a 9000-point cloud.
+python tools/sanitize_forward.py [precision] [--graph]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from butd_detr_b200 import BeaUTyDETR, _lib, synth
+
+precision = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "fp16"
+graph = "--graph" in sys.argv
+model = BeaUTyDETR(num_queries=32, num_decoder_layers=1, num_encoder_layers=1, text_encoder=None, precision=precision,
+                   cuda_graph=graph)
+synth.fill_state_dict_(model.state_dict(), 0)
+model = model.cuda().eval()
+inputs = {k: v.cuda() for k, v in synth.synth_batch(21, 2, 4096, 16, 32).items()}
+for _ in range(2):
+    ep = model(inputs)
+torch.cuda.synchronize()
+assert torch.isfinite(ep["last_sem_cls_scores"]).all()
+lib = _lib.load()
+B, N, m = 2, 9000, 300
+xyz = torch.from_numpy(synth.synth_scene(3, N, 8)["point_clouds"][:, :3].copy())[None].repeat(B, 1, 1).contiguous().cuda()
+ws = torch.empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8, device="cuda")
+scratch = torch.empty(lib.bd_fps_grid_scratch_bytes(B, N), dtype=torch.uint8, device="cuda")
+idx = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+_lib.call("bd_grid_build", xyz.data_ptr(), 3, B, N, 0.2, ws.data_ptr())
+_lib.call("bd_fps_grid", xyz.data_ptr(), 3, B, N, m, ws.data_ptr(), scratch.data_ptr(), idx.data_ptr())
+cen = torch.empty(B, m, 3, device="cuda")
+_lib.call("bd_gather_rows", xyz.data_ptr(), 3, idx.data_ptr(), B, N, m, 3, cen.data_ptr(), 3)
+out = torch.zeros(B, m, 64, dtype=torch.int32, device="cuda")
+_lib.call("bd_ball_query_grid_query", cen.data_ptr(), xyz.data_ptr(), 3, B, N, m, 0.2, 64, out.data_ptr(), ws.data_ptr())
+big = torch.from_numpy(synth.synth_scene(4, 50000, 8)["point_clouds"][:, :3].copy())[None].contiguous().cuda()
+i2 = torch.zeros(1, 256, dtype=torch.int32, device="cuda")
+_lib.call("bd_fps", big.data_ptr(), 3, 1, 50000, 256, None, i2.data_ptr())  # 16-CTA cluster kernel (DSMEM st.async)
+torch.cuda.synchronize()
+print("sanitize target finished:", precision, "graph" if graph else "eager", int(idx.sum()), int(out.sum()), int(i2.sum()))
