@@ -81,9 +81,10 @@ def test_module_surface(cuda_lib, golden_dir):
     with pytest.raises(RuntimeError, match="CPU not supported"):
         model({"point_clouds": torch.zeros(1, 1024, 6), "text_hidden": torch.zeros(1, 4, 768),
                "text_attention_mask": torch.ones(1, 4, dtype=torch.long)})
-    model.train()
+    model.train()  # the training forward exists (tests/test_gpu_train.py); the attention-only entry is eval only
     with pytest.raises(NotImplementedError):
-        model({"point_clouds": torch.zeros(1, 1024, 6).cuda()})
+        model({"seed_features": torch.zeros(1, 288, 1024).cuda(), "text_hidden": torch.zeros(1, 4, 768).cuda(),
+               "text_attention_mask": torch.ones(1, 4, dtype=torch.long).cuda()})
 
 
 def test_batch_rows_are_independent(cuda_lib):

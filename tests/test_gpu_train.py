@@ -1,0 +1,149 @@
+"""Training step: the train-mode forward and its gradients against the
+UNMODIFIED reference model's autograd (baseline/_ref copy, its PointNet++ modules on this package's
+`pointnet2._ext` drop-in), the flat gradient arena, and a full optimisation step through the
+reference's own loss."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(n_points=4096, num_queries=32, n_tokens=16, n_boxes=32, dec=2, batch=2, seed=19)
+
+
+@pytest.fixture(scope="module")
+def ref(cuda_lib):
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference Python not installed (python baseline/install_ref.py in the build container)")
+    from butd_detr_b200 import pointnet2_ext
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return ref_loader, ref_loader.import_reference(ext=pointnet2_ext)
+
+
+def _models(ref):
+    from butd_detr_b200 import BeaUTyDETR, pointnet2_ext, synth
+    ref_loader, _ = ref
+    ours = BeaUTyDETR(num_queries=CFG["num_queries"], num_decoder_layers=CFG["dec"], text_encoder=None)
+    sd = synth.fill_state_dict_(ours.state_dict(), 0)
+    ours = ours.cuda()
+    theirs = ref_loader.build_reference_model(ext=pointnet2_ext, num_queries=CFG["num_queries"],
+                                              num_decoder_layers=CFG["dec"])
+    theirs.load_state_dict(dict(sd), strict=False)
+    theirs = theirs.cuda()
+    inputs = {k: v.cuda() for k, v in synth.synth_batch(CFG["seed"], CFG["batch"], CFG["n_points"], CFG["n_tokens"],
+                                                        CFG["n_boxes"]).items()}
+    return ours, theirs, inputs
+
+
+def _scalar(ep, dec):
+    """A loss that touches every graded output (fixed random projections would do no better)."""
+    prefixes = ["proposal_", "last_"] + [f"{i}head_" for i in range(dec - 1)]
+    loss = ep["proj_tokens"].square().mean() + ep["seeds_obj_cls_logits"].sigmoid().mean()
+    for p in prefixes:
+        loss = loss + ep[p + "center"].square().mean() + ep[p + "pred_size"].abs().mean()
+        loss = loss + ep[p + "sem_cls_scores"].log_softmax(-1)[..., 3].mean() * 0.1 + ep[p + "proj_queries"][..., :7].sum(-1).mean()
+    return loss
+
+
+def test_train_forward_and_gradients_match_reference_autograd(ref):
+    """model.train() with every dropout off (the reference's nn.Dropout / attention dropout set to 0):
+    BatchNorm on batch statistics, same end_points, same gradients, same running statistics."""
+    ref_loader, _ = ref
+    ours, theirs, inputs = _models(ref)
+    ours.train()
+    ours.train_dropout = False
+    theirs.train()
+    for mod in theirs.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
+    ep = ours(inputs)
+    ref_in = {"point_clouds": inputs["point_clouds"], "text": (inputs["text_hidden"], inputs["text_attention_mask"]),
+              "det_boxes": inputs["det_boxes"], "det_bbox_label_mask": inputs["det_bbox_label_mask"],
+              "det_class_ids": inputs["det_class_ids"]}
+    ep_ref = theirs(ref_in)
+    worst = 0.0
+    for k, w in ep_ref.items():
+        if torch.is_tensor(w) and w.dtype.is_floating_point:
+            worst = max(worst, float((ep[k].float() - w.float()).abs().max()))
+        elif torch.is_tensor(w):
+            assert torch.equal(ep[k].to(w.dtype), w), k
+    print("train-mode forward vs reference: max abs err", worst)
+    assert worst <= 1e-3
+    _scalar(ep, CFG["dec"]).backward()
+    _scalar(ep_ref, CFG["dec"]).backward()
+    ref_params = dict(theirs.named_parameters())
+    checked, worst_rel = 0, 0.0
+    for n, p in ours.named_parameters():
+        if n.startswith("text_encoder.") or n not in ref_params:
+            continue
+        g, gr = p.grad, ref_params[n].grad
+        assert (g is None) == (gr is None), n
+        if g is None:
+            continue
+        denom = float(gr.abs().max()) + 1e-6
+        rel = float((g - gr).abs().max()) / denom
+        worst_rel = max(worst_rel, rel)
+        assert rel <= 2e-3 or float((g - gr).abs().max()) <= 1e-6, (n, rel)
+        checked += 1
+    print(f"gradients of {checked} parameters vs reference autograd: worst relative error {worst_rel:.2e}")
+    assert checked > 300
+    bufs = dict(theirs.named_buffers())
+    for n, b in ours.named_buffers():
+        if n.endswith("running_mean") or n.endswith("running_var"):
+            torch.testing.assert_close(b, bufs[n], rtol=1e-4, atol=1e-5)
+
+
+def test_training_step_with_reference_loss_arena_and_optimizer(ref):
+    """A whole step the way main_utils.py:401-456 does it — forward (dropout on), the reference's
+    compute_hungarian_loss, backward into the flat arena, the single all-reduce (one rank here), AdamW —
+    lowers the loss on a fixed batch; the eval engine then sees the updated weights."""
+    import torch.distributed as dist
+    from butd_detr_b200.train import GradArena
+    from test_gpu_reference_consumers import _ground_truth
+    _, models = ref
+    ours, _, inputs = _models(ref)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29541")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        gt = _ground_truth(inputs, CFG["n_points"])
+        set_criterion = models.SetCriterion(matcher=models.HungarianMatcher(1, 0, 2, True),
+                                            losses=["boxes", "labels", "contrastive_align"], eos_coef=0.1,
+                                            temperature=0.07).cuda()
+        ours.eval()
+        with torch.no_grad():
+            before = ours(inputs)["last_center"].clone()
+        ours.train()
+        arena = GradArena(ours)
+        opt = torch.optim.AdamW([p for _, p in arena.params], lr=2e-4)
+        losses = []
+        for step in range(6):
+            arena.zero()
+            ep = ours(inputs)
+            for k in gt:
+                assert k not in ep
+                ep[k] = gt[k]
+            loss, _ = models.compute_hungarian_loss(ep, CFG["dec"], set_criterion, query_points_obj_topk=4)
+            loss.backward()
+            assert arena.check_views()
+            arena.all_reduce()
+            torch.nn.utils.clip_grad_norm_([p for _, p in arena.params], 0.1)  # main_utils.py:433-436
+            opt.step()
+            losses.append(float(loss))
+        print("losses:", ["%.3f" % l for l in losses], "arena MB:", arena.nbytes / 1e6)
+        assert np.isfinite(losses).all() and min(losses[3:]) < losses[0]
+        ours.eval()
+        with torch.no_grad():
+            after = ours(inputs)["last_center"]
+        assert float((after - before).abs().max()) > 0  # the engine re-packed the updated weights
+    finally:
+        if created:
+            dist.destroy_process_group()
