@@ -210,6 +210,8 @@ def main():
                          "BASELINE.json configs[1] names, outputs within its 1e-2 gate (default); bf16x3 = tcgen05 "
                          "with bf16 hi/lo split operands, outputs within the fp32 gate 1e-3; fp32 = SIMT kernels")
     ap.add_argument("--cpu-scenes", type=int, default=3, help="scenes timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the configs[2] measurement (training step at global batch 8 with the gradient all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -420,6 +422,13 @@ def main():
                "unit": "scenes/s", "steps": 5, "output_gate": PARITY_GATE[other]}
         del m2
 
+    # ---------------- configs[2]: one training step at GLOBAL batch 8, data-parallel, ONE gradient all-reduce
+    train_step = None
+    if not args.no_train_step:
+        del model
+        torch.cuda.empty_cache()
+        train_step = measure_train_step(dev, rank, world, pool_dev)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_scenes > 0:  # the CPU arm is timed at N = 1 only
         threads = os.cpu_count()
@@ -441,7 +450,7 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "latency_b1": latency, "other_precision": alt,
-                "parity": parity,
+                "parity": parity, "train_step": train_step,
                 "attention": attention_summary(scenes / (ms_total * 1e-3) / world, rooflines if kernel_table else []),
                 "rooflines_top": rooflines[:6] if kernel_table else None,
                 "kernels": kernel_table[:40] if kernel_table else None}
@@ -449,6 +458,71 @@ def main():
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_train_step(dev, rank, world, pool_dev, global_batch=8, steps=4, warmup=2):
+    """BASELINE.json configs[2]: batch 8 of configs[1], sharded data-parallel over the ranks, one
+    training step = train-mode forward (batch-statistics BatchNorm, dropout) + backward into the flat
+    gradient arena + ONE all-reduce of the arena (NCCL) + SGD update.  Strong scaling: the global batch
+    stays 8.  The loss is a synthetic scalar over the graded outputs (the reference's loss lives in
+    the reference repo).  Timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from butd_detr_b200 import synth
+    from butd_detr_b200.model import BeaUTyDETR
+    from butd_detr_b200.train import GradArena
+    per = max(1, global_batch // world)
+    model = BeaUTyDETR(text_encoder=None)
+    synth.fill_state_dict_(model.state_dict(), 0)
+    model = model.to(dev).train()
+    arena = GradArena(model)
+    opt = torch.optim.SGD([p for _, p in arena.params], lr=1e-5)
+    batch = {k: v[:per] for k, v in pool_dev.items()}
+
+    def step():
+        arena.zero()
+        ep = model(batch)
+        loss = ep["proj_tokens"].square().mean()
+        for k, v in ep.items():
+            if k.endswith(("center", "pred_size", "sem_cls_scores", "proj_queries")):
+                loss = loss + v.square().mean()
+        loss.backward()
+        arena.all_reduce()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(5):
+        arena.all_reduce()
+    a1.record()
+    torch.cuda.synchronize()
+    ar_ms = a0.elapsed_time(a1) / 5
+    t = torch.tensor([ms, ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    finite = bool(torch.isfinite(loss))
+    arena_bytes = arena.nbytes
+    del model, arena, opt
+    torch.cuda.empty_cache()
+    return {"workload": "configs[2]: training step, global batch %d (%d per GPU), fwd + bwd + one all-reduce + SGD" % (per * world, per),
+            "scaling": "strong", "global_batch": per * world, "ms_per_step": float(t[0]),
+            "scenes_per_s": per * world / (float(t[0]) * 1e-3), "grad_allreduce_ms": float(t[1]) if world > 1 else 0.0,
+            "grad_arena_bytes": arena_bytes,
+            "collectives_per_step": 1 if world > 1 else 0, "loss_finite": finite,
+            "dense_layers": "PyTorch operators (autograd); point operators fwd + bwd: libbutd_b200 kernels"}
 
 
 def attention_summary(scenes_per_s_per_gpu, rooflines):
