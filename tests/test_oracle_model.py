@@ -60,11 +60,13 @@ def test_module_state_dict_matches_reference_schema(golden_dir):
     assert any("backbone_net" in k for k in params)
 
 
-def test_module_refuses_cpu_and_training():
+def test_module_refuses_cpu_tensors_in_both_modes():
+    """No CPU path: the eval engine and the training forward (point operators on the CUDA kernels) both
+    refuse host tensors the way the reference's ops do ("CPU not supported", ball_query.cpp:32-34)."""
     model = BeaUTyDETR(text_encoder=None, num_decoder_layers=1, num_encoder_layers=1).eval()
     x = {"point_clouds": torch.zeros(1, 1024, 6), "text_hidden": torch.zeros(1, 4, 768),
          "text_attention_mask": torch.ones(1, 4, dtype=torch.long)}
     with pytest.raises(RuntimeError, match="CPU not supported"):
         model(x)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CPU not supported"):
         model.train()(x)
