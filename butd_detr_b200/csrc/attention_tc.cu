@@ -351,7 +351,11 @@ __global__ void __launch_bounds__(AT_THREADS, STAGES == 1 ? 2 : 1) attention_tc_
 // While one tile's warps do their softmax the tensor pipe runs the other tile's two MMAs
 // (ping-pong), so MUFU / FMA work and tensor work overlap inside one CTA.
 // TMEM columns: [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,304) Ot_0, [320,368) Ot_1.
-constexpr int WS_THREADS = 384, WS_BK = 128;
+// TILES = 1 (short key sequences): one query tile per CTA, 6 warps (loader, MMA issuer, four softmax
+// warps), 256 TMEM columns ([0,128) S / P, [128,176) Ot) and ~61 KB of shared memory, so TWO CTAs share an
+// SM: with one or two key tiles a CTA is a serial chain (load -> S -> softmax -> P.V -> write-out) and
+// the second CTA is what fills its gaps.
+constexpr int WS_THREADS = 384, WS_THREADS1 = 192, WS_BK = 128;
 
 // second softmax pass over one 128-key score row held in TMEM (see attention_ws_kernel)
 template <int PARTS, bool MASKED>
@@ -393,14 +397,16 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long ne
   }
 }
 
-template <int PARTS>
-__global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnParams p) {
+template <int PARTS, int TILES>
+__global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES == 2 ? 1 : 2) attention_ws_kernel(const AttnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t K_PART = k_part(WS_BK), V_PART = v_part(WS_BK);
   constexpr uint32_t Q_TILE = PARTS * QK_PART, K_TILE = PARTS * K_PART, V_TILE = PARTS * V_PART;
-  unsigned char *sQ = smem;               // 2 query tiles
-  unsigned char *sK = sQ + 2 * Q_TILE;    // 2 stages
+  unsigned char *sQ = smem;                   // TILES query tiles
+  unsigned char *sK = sQ + TILES * Q_TILE;    // 2 stages
+  constexpr int SM0 = TILES == 2 ? 4 : 2;     // first softmax warp
+  constexpr uint32_t TM_COLS = TILES == 2 ? 512 : 256, TM_O = TILES == 2 ? 256 : 128;
   unsigned char *sV = sK + 2 * K_TILE;    // 2 stages
   __shared__ __align__(8) unsigned long long bar_q, bar_kf[2], bar_ke[2], bar_vf[2], bar_ve[2], bar_s[2], bar_p[2];
   __shared__ uint32_t tmem_base_s;
@@ -408,14 +414,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
   const int lane = tid & 31;
-  const int b = blockIdx.z, h = blockIdx.y, qt0 = blockIdx.x * 2;
-  const int nt = min(2, p.nq - qt0);  // query tiles of this CTA
+  const int b = blockIdx.z, h = blockIdx.y, qt0 = blockIdx.x * TILES;
+  const int nt = min(TILES, p.nq - qt0);  // query tiles of this CTA
   const int nk = p.nk;
   const size_t bh = static_cast<size_t>(b) * p.H + h;
 
-  if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), TM_COLS);
   if (tid == 32) {
-    tc::mbar_init(tc::smem_u32(&bar_q), 8);
+    tc::mbar_init(tc::smem_u32(&bar_q), 4 * TILES);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tc::smem_u32(&bar_kf[i]), 1);
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
     tc::mbar_wait(tc::smem_u32(&bar_q), 0);
     for (int j = 0; j <= nk; ++j) {  // iteration j: P.V of key tile j-1, then Q.K^T of key tile j
       for (int t = 0; t < nt; ++t) {
-        const uint32_t tS = tmem + t * 128, tO = tmem + 256 + t * 64;
+        const uint32_t tS = tmem + t * 128, tO = tmem + TM_O + t * 64;
         if (j > 0) {
           const int jj = j - 1, st = jj & 1;
           tc::mbar_wait(tc::smem_u32(&bar_p[t]), jj & 1);
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= SM0) {
     // ----------------------------------------------------------------------- softmax warps
     // First, while the K / V tiles are in flight: the CTA's own Q rows, fp32 -> bf16 hi / lo
     // (softmax scale * log2 e folded in) straight into the operand tiles — a Q tile has exactly
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
     // of 8 head dims); chunks 0..5 cover the three K = 16 steps (36 dims, rest zero).
     {
       const float *Qg = p.Q + b * p.sq_b + h * AT_HD;
-      for (int e = tid - 128; e < nt * AT_BM * 6; e += 256) {
+      for (int e = tid - SM0 * 32; e < nt * AT_BM * 6; e += TILES * 128) {
         const int rr = e / 6, ch = e - rr * 6;  // rr = row within the CTA's nt * 128 queries
         const int q = qt0 * AT_BM + rr;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -535,11 +541,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_q));
     }
-    if (((warp - 4) >> 2) < nt) {
-    const int t = (warp - 4) >> 2;
+    if (((warp - SM0) >> 2) < nt) {
+    const int t = (warp - SM0) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem + lane_base + t * 128, tO = tmem + lane_base + 256 + t * 64;
+    const uint32_t tS = tmem + lane_base + t * 128, tO = tmem + lane_base + TM_O + t * 64;
     const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
     float m_run = -INFINITY, corr_prev = 1.f;
     float o_acc[40];  // [0,36) output dims, [36] running softmax denominator, rest padding
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+  if (warp == 0) tc::tmem_dealloc(tmem, TM_COLS);
 }
 
 }  // namespace
@@ -651,6 +657,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attention_ws_kernel(const AttnP
 // Implementation switch (A/B measurements and the parity tests of both kernels): 1 = the
 // warp-specialised kernel above (default), 0 = the first-generation single-role kernel.
 static int g_attn_impl = 1, g_attn_dbg = 0;
+// key tiles (of 128) up to which the one-tile-per-CTA, two-CTAs-per-SM variant runs in the fp16 mode.  Measured at
+// 128 scenes (tools/microbench_attention_tiles.py): it wins at EVERY shape of the model — 1024x1024 0.633 vs 0.698 ms,
+// 80x1024 0.159 vs 0.187, 80x80 0.037 vs 0.046 — so the default is "always".  The bf16x3 mode keeps two ping-ponged
+// tiles per CTA: its operand tiles (hi + lo) leave room for one CTA per SM either way.
+static int g_attn_small_nk = 1 << 30;
+extern "C" int bd_attention_tc_set_small_nk(int nk) {
+  g_attn_small_nk = nk;
+  return BD_OK;
+}
 extern "C" int bd_attention_tc_select(int impl) {
   BD_REQUIRE(impl >= 0 && ((impl & 15) == 0 || (impl & 15) == 1), "bd_attention_tc_select: impl must be 0 or 1");
   g_attn_impl = impl & 15;
@@ -703,12 +718,16 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
   p.Kp = p.Qp + static_cast<size_t>(B) * H * p.nq * parts * QK_PART;
   p.Vp = p.Kp + static_cast<size_t>(B) * H * p.nk * parts * k_part(BK);
   constexpr size_t WS_SMEM1 = 2 * (QK_PART + k_part(128) + v_part(128)) + 1024, WS_SMEM2 = 2 * WS_SMEM1 - 1024;
+  // one query tile per CTA: Q tile + two stages of K and V^T
+  constexpr size_t WS_SMEM1S = QK_PART + 2 * (k_part(128) + v_part(128)) + 1024, WS_SMEM2S = 2 * WS_SMEM1S - 1024;
   static bd::PerDeviceOnce configured;  // function attributes are per device
   BD_CUDA(configured.run([&]() {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<1, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1S);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2S);
     return e;
   }), "bd_attention_tc");
   cudaStream_t s = bd::as_stream(stream);
@@ -716,12 +735,19 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
   if (impl == 1) {
     p.skip_q = 1;
     pgrid.x = 2 * p.nk;
+    const bool small = (parts == 1 || g_attn_small_nk < (1 << 30)) && p.nk <= g_attn_small_nk;  // one query tile per CTA, two CTAs per SM
     if (parts == 2) {
       BD_CUDA(bd::launch_pdl(attention_pack_kernel<2, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
-      BD_CUDA(bd::launch_pdl(attention_ws_kernel<2>, wgrid, dim3(WS_THREADS), WS_SMEM2, s, p), "bd_attention_tc");
+      if (small)
+        BD_CUDA(bd::launch_pdl(attention_ws_kernel<2, 1>, grid, dim3(WS_THREADS1), WS_SMEM2S, s, p), "bd_attention_tc");
+      else
+        BD_CUDA(bd::launch_pdl(attention_ws_kernel<2, 2>, wgrid, dim3(WS_THREADS), WS_SMEM2, s, p), "bd_attention_tc");
     } else {
       BD_CUDA(bd::launch_pdl(attention_pack_kernel<1, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
-      BD_CUDA(bd::launch_pdl(attention_ws_kernel<1>, wgrid, dim3(WS_THREADS), WS_SMEM1, s, p), "bd_attention_tc");
+      if (small)
+        BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1>, grid, dim3(WS_THREADS1), WS_SMEM1S, s, p), "bd_attention_tc");
+      else
+        BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 2>, wgrid, dim3(WS_THREADS), WS_SMEM1, s, p), "bd_attention_tc");
     }
   } else if (parts == 2) {
     const size_t smem = 2 * (QK_PART + (k_part(64) + v_part(64)) + p_part(64)) + 1024;

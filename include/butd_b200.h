@@ -260,6 +260,11 @@ int bd_set_pdl(int enabled);
  * softmax warpgroups, probabilities kept in TMEM; default), 0 = first-generation kernel (kept for
  * A/B measurements).  Process-wide; not meant to be flipped while launches are in flight. */
 int bd_attention_tc_select(int impl);
+/* Tuning hook: key sequences of at most `nk` tiles of 128 keys run as one query tile per CTA with
+ * two CTAs per SM (256 TMEM columns each); longer ones as two ping-ponged query tiles per CTA.
+ * Default: every length in the fp16 mode (measured faster at all of the model's shapes), none in the
+ * bf16x3 mode; 0 = always the two-tile kernel; any other value applies to both modes. */
+int bd_attention_tc_set_small_nk(int nk);
 
 /* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n
  * logits, indices of the k largest sigmoid values, descending, ties -> lower index. n <= 4096 */

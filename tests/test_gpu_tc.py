@@ -256,3 +256,42 @@ def test_unfused_sa_level_path_matches_fused(cuda_lib, precision):
         torch.testing.assert_close(unfused[k], fused[k], rtol=tol, atol=tol)
     for k in ("sa1_inds", "sa2_inds"):
         assert torch.equal(unfused[k], fused[k])
+
+
+@pytest.mark.parametrize("small_nk", [0, 8])
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 80, True), (3, 256, 132, True), (2, 300, 1000, True),
+                                             (2, 80, 1024, False), (1, 129, 257, False), (5, 80, 80, True)])
+def test_attention_tc_tile_variants(cuda_lib, B, Lq, Lk, masked, split, small_nk):
+    """Both CTA shapes of the warp-specialised kernel on every sequence length: two ping-ponged query
+    tiles per CTA (small_nk = 0) and one query tile per CTA with two CTAs per SM (small_nk = 8)."""
+    H, hd = 8, 36
+    E = H * hd
+    lib = cuda_lib.load()
+    g = _g(Lq * 11 + Lk + small_nk)
+    q = torch.randn(B, Lq, E, device="cuda", generator=g)
+    kv = torch.randn(B, Lk, 2 * E, device="cuda", generator=g)
+    k, v = kv[..., :E], kv[..., E:]
+    mask = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), generator=torch.Generator().manual_seed(Lk))
+        mask = (torch.arange(Lk)[None] >= lens[:, None]).cuda()
+    out = torch.full((B, Lq, E), float("nan"), device="cuda")
+    m8 = mask.to(torch.uint8).contiguous() if masked else None
+    ws = torch.empty(lib.bd_attention_tc_workspace_bytes(B, H, Lq, Lk, split), dtype=torch.uint8, device="cuda")
+    lib.bd_attention_tc_set_small_nk(small_nk)
+    try:
+        cuda_lib.call("bd_attention_tc", q.data_ptr(), E, Lq * E, k.data_ptr(), 2 * E, Lk * 2 * E, v.data_ptr(), 2 * E,
+                      Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), split,
+                      ws.data_ptr())
+    finally:
+        lib.bd_attention_tc_set_small_nk(1 << 30)
+    qh = q.reshape(B, Lq, H, hd).transpose(1, 2).double()
+    kh = k.reshape(B, Lk, H, hd).transpose(1, 2).double()
+    vh = v.reshape(B, Lk, H, hd).transpose(1, 2).double()
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if masked:
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    tol = 5e-3 if split == 1 else 1e-4
+    torch.testing.assert_close(out, want, rtol=tol, atol=tol)
