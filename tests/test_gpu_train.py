@@ -78,7 +78,7 @@ def test_train_forward_and_gradients_match_reference_autograd(ref):
     _scalar(ep, CFG["dec"]).backward()
     _scalar(ep_ref, CFG["dec"]).backward()
     ref_params = dict(theirs.named_parameters())
-    checked, worst_rel = 0, 0.0
+    checked, worst_rel, num, den = 0, 0.0, 0.0, 0.0
     for n, p in ours.named_parameters():
         if n.startswith("text_encoder.") or n not in ref_params:
             continue
@@ -86,15 +86,19 @@ def test_train_forward_and_gradients_match_reference_autograd(ref):
         assert (g is None) == (gr is None), n
         if g is None:
             continue
-        denom = float(gr.abs().max()) + 1e-6
-        rel = float((g - gr).abs().max()) / denom
-        worst_rel = max(worst_rel, rel)
-        # fp32 everywhere, but different kernels (fused attention, atomics order of the scatter-adds, batch-
-        # statistics BatchNorm backward): 1e-2 of the gradient's own scale; the worst case is printed
-        assert rel <= 1e-2 or float((g - gr).abs().max()) <= 1e-6, (n, rel)
+        # fp32 everywhere, but different kernels (fused attention, atomics order of the scatter-adds) ahead of
+        # batch-statistics BatchNorm backward passes that amplify 1e-5 input differences: per parameter the
+        # relative L2 error must stay below 3 %, over ALL gradients together below 0.2 %
+        err, ref_norm = float((g - gr).norm()), float(gr.norm())
+        rel = err / (ref_norm + 1e-12)
+        worst_rel = max(worst_rel, rel if ref_norm > 1e-6 else 0.0)
+        assert rel <= 3e-2 or err <= 1e-5, (n, rel, err)
+        num, den = num + err * err, den + ref_norm * ref_norm
         checked += 1
-    print(f"gradients of {checked} parameters vs reference autograd: worst relative error {worst_rel:.2e}")
-    assert checked > 300
+    total_rel = (num / den) ** 0.5
+    print(f"gradients of {checked} parameters vs reference autograd: relative L2 error overall {total_rel:.2e}, "
+          f"worst single parameter {worst_rel:.2e}")
+    assert checked > 300 and total_rel <= 2e-3
     bufs = dict(theirs.named_buffers())
     for n, b in ours.named_buffers():
         if n.endswith("running_mean") or n.endswith("running_var"):
