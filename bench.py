@@ -226,7 +226,10 @@ def main():
     # communicator lines in particular (NCCL_DEBUG=INFO unless the caller chose a level) — goes to stderr:
     # fd 1 is pointed at fd 2 for the whole run and the JSON line is written to the saved stdout at the end.
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        # communicator set-up lines ("comm ... rank r nranks N ... Init COMPLETE") on stderr, so that the ranks of
+        # the job can be checked from the outside; INIT only, to keep the volume down
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
