@@ -377,6 +377,9 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
     float cb = -1.0f;  // lane candidate: distance, key, coordinates
     uint32_t cl = 0u;
     float ccx = 0.f, ccy = 0.f, ccz = 0.f;
+    bool refresh = false;  // full pass this round: copies of the lane's own-bucket candidate for the refresh below
+    float r_cb = -1.0f, r_x = 0.f, r_y = 0.f, r_z = 0.f, r_max = -1.0f;
+    uint32_t r_cl = 0u;
     bool slab_far;
     {
       const float ex = fmaxf(fabsf(x1 - sbx) - shx, 0.f), ey = fmaxf(fabsf(y1 - sby) - shy, 0.f),
@@ -419,14 +422,10 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
         }
       }
       if (cbk >= 0) ccx = S.cx[cbk], ccy = S.cy[cbk], ccz = S.cz[cbk];
-      // refresh the slab's cached winner (over the buckets that are NOT being visited) and bound
-      const uint32_t ch = dist_key(cb);
-      own_h = __reduce_max_sync(FULL, ch);
-      own_l = __reduce_max_sync(FULL, ch == own_h ? cl : 0u);
-      const int src = __ffs(__ballot_sync(FULL, ch == own_h && (cl == own_l || own_h == 0u))) - 1;
-      own_x = __shfl_sync(FULL, ccx, src), own_y = __shfl_sync(FULL, ccy, src), own_z = __shfl_sync(FULL, ccz, src);
-      slab_best = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(lane_max, 0.f))));  // >= 0: bits order = value order
-      if (__all_sync(FULL, lane_max < 0.f)) slab_best = -1.0f;
+      // the slab's cached winner (over the buckets that are NOT being visited) and bound are refreshed from
+      // these copies AFTER the warp has posted — off the round's critical path
+      refresh = true;
+      r_cb = cb, r_cl = cl, r_x = ccx, r_y = ccy, r_z = ccz, r_max = lane_max;
       slab_dirty = total != 0;  // visited buckets are missing from the cached winner: recompute next round
     }
     if (tid == 0) S.count[pp ^ 1] = 0u;  // last read before the previous round's posts
@@ -483,6 +482,15 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(smem_u32(&S.bar));
+    }
+    if (refresh) {  // warp-uniform; runs while the other warps are still posting
+      const uint32_t ch = dist_key(r_cb);
+      own_h = __reduce_max_sync(FULL, ch);
+      own_l = __reduce_max_sync(FULL, ch == own_h ? r_cl : 0u);
+      const int src = __ffs(__ballot_sync(FULL, ch == own_h && (r_cl == own_l || own_h == 0u))) - 1;
+      own_x = __shfl_sync(FULL, r_x, src), own_y = __shfl_sync(FULL, r_y, src), own_z = __shfl_sync(FULL, r_z, src);
+      slab_best = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(r_max, 0.f))));  // >= 0: bits order = value order
+      if (__all_sync(FULL, r_max < 0.f)) slab_best = -1.0f;
     }
     FPS_T(3);
     // ---- all warps have posted: the CTA's winner is the next sample

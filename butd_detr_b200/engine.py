@@ -88,7 +88,7 @@ def _plain(sd, name):
 FPS_GRID_MIN_BATCH = 38  # scenes from which SA1's FPS runs as the bucketed one-CTA-per-scene kernel over the cell list
 # (bd_fps_grid: a single wave up to 148 scenes, 3.4 - 3.95 ms whatever the batch) instead of the register-resident
 # cluster kernel (37 scenes per wave of 2.18 ms: 4.36 ms at 64 scenes, 8.72 ms at 128)
-DECODER_SPLIT_MIN = 1 << 30  # scenes per half above which the decoder would run as two batch halves on two streams:
+DECODER_SPLIT_MIN = int(__import__("os").environ.get("BUTD_DECODER_SPLIT_MIN", 1 << 30))  # scenes per half above which the decoder would run as two batch halves on two streams:
 # measured at 32 scenes: 2336 vs 2400 scenes/s — no gain (the kernels of one half already fill a wave), so it is off
 FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
