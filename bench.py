@@ -386,6 +386,7 @@ def main():
             ach = units / (r["mean_ms"] * 1e-3) / (1e9 if bound == "hbm" else 1e12)
             rooflines.append({"kernel": r["name"], "launches": r["launches"], "bound": bound, "achieved": ach, "peak": pk, "unit": unit,
                               "frac": ach / pk, "traffic": measured_traffic(r["name"].split("(")[0], B),
+                              "traffic_captured_at_batch": traffic_batch(r["name"].split("(")[0]),
                               "peak_source": peak_src,
                               "algorithmic_units_per_launch": units, "mean_launch_ms": r["mean_ms"],
                               "share_of_step": r["share"]})
@@ -587,17 +588,27 @@ def algorithmic_work(name, a):
 
 
 def measured_traffic(name, B):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's dominant kernel
-    from the committed `ncu --set full` capture (profiles/r01_traffic.json: captured at the batch
-    size named there; None when the capture is for another batch size or kernel)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's dominant kernel from the
+    committed `ncu --set full` capture (profiles/r02_traffic.json).  The capture was taken at the batch size
+    named there; for another batch size the per-scene traffic is scaled to this run's batch (every kernel of
+    the path works scene by scene) — `roofline.traffic_captured_at_batch` says which."""
     p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(p):
         p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(p):
         return None
-    d = json.load(open(p))
-    e = d.get(name)
-    return e["dram_bytes_per_launch"] if e and e.get("batch") == B else None
+    e = json.load(open(p)).get(name)
+    if not e:
+        return None
+    return int(e["dram_bytes_per_launch"] * B / e["batch"])
+
+
+def traffic_batch(name):
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(name)
+    return e["batch"] if e else None
 
 
 def algorithmic_bytes(kernel, B):
