@@ -688,10 +688,42 @@ extern "C" long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int L
   return static_cast<long long>(B) * H * parts * (nq * QK_PART + nk * (k_part(BK) + v_part(BK)));
 }
 
+// phase: 1 = pack K / V into the workspace, 2 = attention over a packed workspace, 3 = both
+static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
+                               const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
+                               float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
+                               int split, void *workspace, bd_stream_t stream, int phase);
+
 extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
                                const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
                                float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
                                int split, void *workspace, bd_stream_t stream) {
+  return attention_tc_phases(Q, ldq, sq_b, K, ldk, sk_b, V, ldv, sv_b, key_padding_mask, O, ldo, so_b, B, H, Lq, Lk, hd,
+                             scale, split, workspace, stream, 3);
+}
+
+// The two halves of bd_attention_tc for keys / values that are known long before their queries (the
+// decoder's memory K / V): pack once, on another stream, off the critical path; attend later.  Same Lq,
+// Lk, split and workspace in both calls (the workspace layout depends on them).
+extern "C" int bd_attention_tc_pack_kv(const float *K, int ldk, long long sk_b, const float *V, int ldv, long long sv_b,
+                                       int B, int H, int Lq, int Lk, int hd, int split, void *workspace,
+                                       bd_stream_t stream) {
+  BD_REQUIRE(g_attn_impl == 1, "bd_attention_tc_pack_kv: only with the warp-specialised kernel");
+  return attention_tc_phases(K, 4, 0, K, ldk, sk_b, V, ldv, sv_b, nullptr, reinterpret_cast<float *>(workspace), 4, 0, B, H,
+                             Lq, Lk, hd, 1.0f, split, workspace, stream, 1);
+}
+extern "C" int bd_attention_tc_packed(const float *Q, int ldq, long long sq_b, const unsigned char *key_padding_mask,
+                                      float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd,
+                                      float scale, int split, void *workspace, bd_stream_t stream) {
+  BD_REQUIRE(g_attn_impl == 1, "bd_attention_tc_packed: only with the warp-specialised kernel");
+  return attention_tc_phases(Q, ldq, sq_b, Q, 4, 0, Q, 4, 0, key_padding_mask, O, ldo, so_b, B, H, Lq, Lk, hd, scale, split,
+                             workspace, stream, 2);
+}
+
+static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
+                               const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
+                               float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
+                               int split, void *workspace, bd_stream_t stream, int phase) {
   BD_REQUIRE(Q && K && V && O && workspace, "bd_attention_tc: null pointer");
   BD_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && B <= 65535 && H <= 65535, "bd_attention_tc: bad sizes");
   BD_REQUIRE(hd == AT_HD, "bd_attention_tc: built for head_dim 36 (d_model 288 / 8 heads)");
@@ -737,14 +769,16 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
     pgrid.x = 2 * p.nk;
     const bool small = (parts == 1 || g_attn_small_nk < (1 << 30)) && p.nk <= g_attn_small_nk;  // one query tile per CTA, two CTAs per SM
     if (parts == 2) {
-      BD_CUDA(bd::launch_pdl(attention_pack_kernel<2, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
-      if (small)
+      if (phase & 1) BD_CUDA(bd::launch_pdl(attention_pack_kernel<2, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
+      if (!(phase & 2)) {
+      } else if (small)
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<2, 1>, grid, dim3(WS_THREADS1), WS_SMEM2S, s, p), "bd_attention_tc");
       else
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<2, 2>, wgrid, dim3(WS_THREADS), WS_SMEM2, s, p), "bd_attention_tc");
     } else {
-      BD_CUDA(bd::launch_pdl(attention_pack_kernel<1, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
-      if (small)
+      if (phase & 1) BD_CUDA(bd::launch_pdl(attention_pack_kernel<1, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
+      if (!(phase & 2)) {
+      } else if (small)
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1>, grid, dim3(WS_THREADS1), WS_SMEM1S, s, p), "bd_attention_tc");
       else
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 2>, wgrid, dim3(WS_THREADS), WS_SMEM1, s, p), "bd_attention_tc");

@@ -364,7 +364,31 @@ class ForwardEngine:
             _lib.call("bd_attention_f32", *args)
         return out
 
-    def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False, res=None, ln_key=None, kv=None):
+    def pack_kv(self, kv, B, Lq, Lk):
+        """K / V^T operand tiles of a fused (B*Lk, 2E) key-value projection, packed ahead of time (the
+        decoder's memory K / V: on kv_stream, off the critical path).  None when the tensor-core
+        attention does not apply."""
+        E, H = self.d_model, self.n_heads
+        hd = E // H
+        k, v = kv[:, :E], kv[:, E:]
+        if self.precision == "fp32" or hd != 36 or k.stride(0) % 4 or k.data_ptr() % 16 or v.data_ptr() % 16:
+            return None
+        ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
+        _lib.call("bd_attention_tc_pack_kv", k.data_ptr(), k.stride(0), Lk * k.stride(0), v.data_ptr(), v.stride(0),
+                  Lk * v.stride(0), B, H, Lq, Lk, hd, self.split, ws.data_ptr())
+        return ws
+
+    def attention_packed(self, q, ws, B, Lq, Lk, mask):
+        """attention() over K / V tiles packed by pack_kv (same B, Lq, Lk)."""
+        E, H = self.d_model, self.n_heads
+        hd = E // H
+        out = self._empty(B * Lq, E)
+        _lib.call("bd_attention_tc_packed", q.data_ptr(), q.stride(0), Lq * q.stride(0), _lib.ptr(mask), out.data_ptr(), E,
+                  Lq * E, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), self.split, ws.data_ptr())
+        return out
+
+    def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False, res=None, ln_key=None, kv=None,
+            packed=None):
         """nn.MultiheadAttention (eval) incl. in/out projections.  q = x_q (+pos_q);
         k = x_kv (+pos_k); v = x_kv.  Returns LayerNorm(res + out_proj(attention)) — the
         post-LN residual block every call site of the reference wraps around the attention."""
@@ -385,6 +409,9 @@ class ForwardEngine:
         else:  # cross attention: k = v = memory (no positional term in this model)
             q = self.lin(x_q, key + ".q", add=pos_q)
             assert pos_k is None
+            if packed is not None and q.stride(0) % 4 == 0 and q.data_ptr() % 16 == 0:
+                # memory K / V projected AND packed earlier on kv_stream
+                return self.lin_ln(self.attention_packed(q, packed, B, Lq, Lk, mask), key + ".o", res, ln_key)
             if kv is None:  # else: projected earlier on kv_stream
                 kv = self.lin(x_kv, key + ".kv")
             k, v = kv[:, :E], kv[:, E:]
@@ -746,7 +773,14 @@ class ForwardEngine:
                     kv_l = self.lin(text, k + ".l.kv")
                     kv_d = self.lin(det, k + ".d.kv") if cfg["butd"] else None
                     kv_v = self.lin(vis, k + ".v.kv")
-                    mem_kv.append((kv_l, kv_d, kv_v, kvs.record_event()))
+                    # ... and their K / V^T operand tiles: the decoder's attention calls then start at the
+                    # attention kernel itself (whole batch only: the tile image is not sliceable by scene)
+                    Qn = cfg["num_queries"]
+                    packs = (None, None, None)
+                    if B < 2 * DECODER_SPLIT_MIN:
+                        packs = (self.pack_kv(kv_l, B, Qn, L), self.pack_kv(kv_d, B, Qn, D) if cfg["butd"] else None,
+                                 self.pack_kv(kv_v, B, Qn, V))
+                    mem_kv.append((kv_l, kv_d, kv_v, kvs.record_event(), packs))
             ep["text_memory"] = text.view(B, L, E)
             ep["seed_features"] = vis.view(B, V, E).transpose(1, 2)
             if cfg["contrastive_align_loss"]:  # nothing downstream reads it: off the critical path
@@ -804,7 +838,7 @@ class ForwardEngine:
                 for i in range(nd):
                     k = f"dec{i}"
                     torch.cuda.nvtx.range_push(f"butd/decoder_layer{i}") if NVTX else None
-                    kv_l, kv_d, kv_v, kv_ready = mem_kv[i]
+                    kv_l, kv_d, kv_v, kv_ready, (pk_l, pk_d, pk_v) = mem_kv[i]
                     if spe == "loc_learned":  # query_pos = cat(base_xyz, base_size)  (bdetr.py:287)
                         qp_in = self._empty(nb * Q, 6)
                         _lib.call("bd_concat_rows", base_xyz.data_ptr(), 3, 3, base_size.data_ptr(), 3, 3,
@@ -817,12 +851,12 @@ class ForwardEngine:
                     q = self.mha(k + ".self", q, qpos, q, qpos, nb, Q, Q, None, True, q, k + ".norm1")
                     cur.wait_event(kv_ready)
                     q = self.mha(k + ".l", q, qpos, None, None, nb, Q, L, tm, False, q, k + ".norm_l",
-                                 kv=rows(kv_l, b0, b1, L))
+                                 kv=rows(kv_l, b0, b1, L), packed=pk_l)
                     if cfg["butd"]:
                         q = self.mha(k + ".d", q, qpos, None, None, nb, Q, D, dm, False, q, k + ".norm_d",
-                                     kv=rows(kv_d, b0, b1, D))
+                                     kv=rows(kv_d, b0, b1, D), packed=pk_d)
                     q = self.mha(k + ".v", q, qpos, None, None, nb, Q, V, None, False, q, k + ".norm_v",
-                                 kv=rows(kv_v, b0, b1, V))
+                                 kv=rows(kv_v, b0, b1, V), packed=pk_v)
                     q = self.ffn(q, k + ".ffn", k + ".norm2")
                     o = {k2: rows(v2, b0, b1, Q) for k2, v2 in outs[prefixes[i + 1]].items()}
                     if cfg["contrastive_align_loss"]:

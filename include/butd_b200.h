@@ -260,6 +260,17 @@ int bd_set_pdl(int enabled);
  * softmax warpgroups, probabilities kept in TMEM; default), 0 = first-generation kernel (kept for
  * A/B measurements).  Process-wide; not meant to be flipped while launches are in flight. */
 int bd_attention_tc_select(int impl);
+/* The two halves of bd_attention_tc, for keys / values that exist long before their queries (the
+ * decoder's memory K / V): bd_attention_tc_pack_kv writes the K / V^T operand tiles into `workspace`
+ * (any stream, any time after K / V are complete), bd_attention_tc_packed attends over them.  Same
+ * B, H, Lq, Lk, split and workspace in both calls. */
+int bd_attention_tc_pack_kv(const float *K, int ldk, long long sk_b, const float *V, int ldv,
+                            long long sv_b, int B, int H, int Lq, int Lk, int hd, int split,
+                            void *workspace, bd_stream_t stream);
+int bd_attention_tc_packed(const float *Q, int ldq, long long sq_b,
+                           const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
+                           int B, int H, int Lq, int Lk, int hd, float scale, int split,
+                           void *workspace, bd_stream_t stream);
 /* Tuning hook: key sequences of at most `nk` tiles of 128 keys run as one query tile per CTA with
  * two CTAs per SM (256 TMEM columns each); longer ones as two ping-ponged query tiles per CTA.
  * Default: every length in the fp16 mode (measured faster at all of the model's shapes), none in the
