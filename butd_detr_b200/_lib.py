@@ -27,8 +27,9 @@ _SIGNATURES = {
     "bd_fps_grid_set_warps": [_I],
     "bd_fps_grid_stats": [_I, _P],
     "bd_attention_tc_set_small_nk": [_I],
-    "bd_attention_tc_pack_kv": [_P, _I, _LL, _P, _I, _LL, _I, _I, _I, _I, _I, _I, _P, _P],
-    "bd_attention_tc_packed": [_P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _F, _I, _P, _P],
+    "bd_attention_tc_pack_kv": [_P, _I, _LL, _P, _I, _LL, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "bd_attention_tc_packed": [_P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P],
+    "bd_attention_tc_h": [_P, _I, _LL, _P, _I, _LL, _P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P],
     "bd_grid_build": [_P, _I, _I, _I, _F, _P, _P],
     "bd_ball_query_grid_query": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P],
     "bd_gather_points": [_P, _P, _I, _I, _I, _I, _P, _P],
@@ -47,6 +48,8 @@ _SIGNATURES = {
     "bd_linear_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "bd_linear_tc": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_linear_ln_tc": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bd_linear_tc_h": [_P, _I, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bd_linear_ln_tc_h": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_linear_tc_set_debug": [_P],
     "bd_sa_group_linear_tc": [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_sa_mlp_tc": [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P],

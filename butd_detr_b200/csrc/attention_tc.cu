@@ -39,8 +39,26 @@ struct AttnParams {
   int Lq, Lk, H, nq, nk;  // nk = key tiles of BK keys
   float scale_log2;
   int skip_q;  // pack kernel: Q tiles are converted inside the attention kernel, start at the K tiles
+  int q16, k16, v16, o16;  // the tensor is fp16 in HBM (leading dimensions / batch strides then count halfs)
   int dbg;  // timing experiments only (bit 0: no softmax arithmetic, bit 1: no P.V MMAs, bit 2: no Q.K^T MMAs)
 };
+
+// 8 consecutive head dims of an fp32 or fp16 row (element offset `off`; `second`: dims 4..7 are inside the head)
+__device__ __forceinline__ void load_chunk8(const float *base, long long off, bool half, bool second, float (&v)[8]) {
+  if (half) {
+    const __half *s = reinterpret_cast<const __half *>(base) + off;  // 8-byte aligned (ld % 4 == 0, head offset 72 h bytes)
+    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(s));
+    const uint2 b = second ? __ldg(reinterpret_cast<const uint2 *>(s + 4)) : make_uint2(0u, 0u);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&a.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&a.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&b.x)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&b.y));
+    v[0] = f0.x, v[1] = f0.y, v[2] = f1.x, v[3] = f1.y, v[4] = f2.x, v[5] = f2.y, v[6] = f3.x, v[7] = f3.y;
+  } else {
+    const float4 *s = reinterpret_cast<const float4 *>(base + off);
+    const float4 a = __ldg(s);
+    const float4 b = second ? __ldg(s + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  }
+}
 
 // ------------------------------------------------------------------------------------------ pack
 // grid.x = nq + 2 * nk : [0,nq) Q tiles, [nq,nq+nk) K tiles, rest V tiles ; grid.y = H ; grid.z = B
@@ -56,7 +74,9 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
     // ---- row tiles (Q or K): item = (row, 16-byte chunk of 8 head dims); chunks 5..7 are padding
     const bool is_q = t < p.nq;
     if (!is_q) t -= p.nq;
-    const float *src = is_q ? p.Q + b * p.sq_b : p.K + b * p.sk_b;
+    const float *src = is_q ? p.Q : p.K;
+    const bool src16 = is_q ? p.q16 : p.k16;
+    const long long src_off = (is_q ? b * p.sq_b : b * p.sk_b) + h * AT_HD;
     const int tile_rows = is_q ? 128 : BK;
     const uint32_t part = is_q ? QK_PART : K_PART;
     const int ld = is_q ? p.ldq : p.ldk, n_rows = is_q ? p.Lq : p.Lk, row0 = t * tile_rows;
@@ -64,28 +84,25 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
     unsigned char *dst = (is_q ? p.Qp + (static_cast<size_t>(b) * p.H + h) * p.nq * (PARTS * QK_PART)
                                : p.Kp + (static_cast<size_t>(b) * p.H + h) * p.nk * (PARTS * K_PART)) +
                          static_cast<size_t>(t) * (PARTS * part);
-    src += h * AT_HD;
     // 128 rows x 6 chunks (the three K = 16 steps read chunks 0..5; 36 dims -> chunks 0..4, chunk 5
     // is zero) = 768 items, 3 per thread, chunk-fastest: the lanes of a warp read ~5 whole rows
     // (144 contiguous bytes each) instead of 32 different ones; loads batched
-    float4 a[3][2];
+    float a[3][8];
     int rr[3], cc[3];
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
       const int e = tid + it * 256;
       const int r = e / 6, ch = e - r * 6;
       rr[it] = r < tile_rows ? r : -1, cc[it] = ch;
-      a[it][0] = a[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < tile_rows && row0 + r < n_rows && ch * 8 < AT_HD) {
-        const float4 *s = reinterpret_cast<const float4 *>(src + static_cast<long long>(row0 + r) * ld + ch * 8);
-        a[it][0] = __ldg(s);
-        if (ch * 8 + 4 < AT_HD) a[it][1] = __ldg(s + 1);
-      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[it][i] = 0.f;
+      if (r < tile_rows && row0 + r < n_rows && ch * 8 < AT_HD)
+        load_chunk8(src, src_off + static_cast<long long>(row0 + r) * ld + ch * 8, src16, ch * 8 + 4 < AT_HD, a[it]);
     }
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
-      const float v[8] = {a[it][0].x * mul, a[it][0].y * mul, a[it][0].z * mul, a[it][0].w * mul,
-                          a[it][1].x * mul, a[it][1].y * mul, a[it][1].z * mul, a[it][1].w * mul};
+      const float v[8] = {a[it][0] * mul, a[it][1] * mul, a[it][2] * mul, a[it][3] * mul,
+                          a[it][4] * mul, a[it][5] * mul, a[it][6] * mul, a[it][7] * mul};
       uint4 hi, lo;
       tc::cvt8(PARTS, v, hi, lo);
       if (rr[it] < 0) continue;
@@ -96,7 +113,8 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
   } else {
     // ---- V^T tile: rows = head dims (48, 36 valid), K = 128 keys in two blocks of 64
     t -= p.nq + p.nk;
-    const float *src = p.V + b * p.sv_b + h * AT_HD;
+    const float *src = p.V + (p.v16 ? 0 : b * p.sv_b + h * AT_HD);
+    const __half *src_h = reinterpret_cast<const __half *>(p.V) + b * p.sv_b + h * AT_HD;
     const int k0 = t * BK;
     unsigned char *dst = p.Vp + ((static_cast<size_t>(b) * p.H + h) * p.nk + t) * (PARTS * V_PART);
     // 48 rows x BK/8 key-chunks items (768 for BK = 128), 3 per thread; item = 8 keys of one head dim
@@ -111,7 +129,9 @@ __global__ void __launch_bounds__(256) attention_pack_kernel(const AttnParams p)
         const int key = k0 + kc * 8 + i;
         // row AT_HD of V^T is all ones: column AT_HD of P.V is then the row sum of P (the softmax
         // denominator comes out of the tensor core with the numerator)
-        v[i] = (d < AT_HD && key < p.Lk) ? __ldg(src + static_cast<long long>(key) * p.ldv + d) : (d == AT_HD ? 1.f : 0.f);
+        v[i] = (d < AT_HD && key < p.Lk)
+                   ? (p.v16 ? __half2float(__ldg(src_h + static_cast<long long>(key) * p.ldv + d)) : __ldg(src + static_cast<long long>(key) * p.ldv + d))
+                   : (d == AT_HD ? 1.f : 0.f);
       }
       uint4 hi, lo;
       tc::cvt8(PARTS, v, hi, lo);
@@ -517,19 +537,15 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
     // one reader, so it never goes through the pack kernel and HBM.  Item = (row, 16-byte chunk
     // of 8 head dims); chunks 0..5 cover the three K = 16 steps (36 dims, rest zero).
     {
-      const float *Qg = p.Q + b * p.sq_b + h * AT_HD;
+      const long long q_off = b * p.sq_b + h * AT_HD;
       for (int e = tid - SM0 * 32; e < nt * AT_BM * 6; e += TILES * 128) {
         const int rr = e / 6, ch = e - rr * 6;  // rr = row within the CTA's nt * 128 queries
         const int q = qt0 * AT_BM + rr;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (q < p.Lq && ch * 8 < AT_HD) {
-          const float4 *src = reinterpret_cast<const float4 *>(Qg + static_cast<long long>(q) * p.ldq + ch * 8);
-          const float4 a0 = __ldg(src);
-          v[0] = a0.x * p.scale_log2, v[1] = a0.y * p.scale_log2, v[2] = a0.z * p.scale_log2, v[3] = a0.w * p.scale_log2;
-          if (ch * 8 + 4 < AT_HD) {
-            const float4 a1 = __ldg(src + 1);
-            v[4] = a1.x * p.scale_log2, v[5] = a1.y * p.scale_log2, v[6] = a1.z * p.scale_log2, v[7] = a1.w * p.scale_log2;
-          }
+          load_chunk8(p.Q, q_off + static_cast<long long>(q) * p.ldq + ch * 8, p.q16, ch * 8 + 4 < AT_HD, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= p.scale_log2;
         }
         uint4 hi, lo;
         tc::cvt8(PARTS, v, hi, lo);
@@ -635,14 +651,20 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
 
     const int q = (qt0 + t) * AT_BM + row;
     if (q < p.Lq) {
-      float *dst = p.O + b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
+      const long long o_off = b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
       const float l_run = o_acc[AT_HD];
       const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
 #pragma unroll
       for (int d = 0; d < AT_HD; d += 4) {
         float4 o4 = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
         if (l_run == 0.f) o4 = make_float4(NAN, NAN, NAN, NAN);
-        *reinterpret_cast<float4 *>(dst + d) = o4;
+        if (p.o16) {  // fp16 rows: the out-projection reads them as its operand (8-byte aligned: ld % 4 == 0)
+          __half2 h0 = __floats2half2_rn(o4.x, o4.y), h1 = __floats2half2_rn(o4.z, o4.w);
+          *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.O) + o_off + d) =
+              make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+        } else {
+          *reinterpret_cast<float4 *>(p.O + o_off + d) = o4;
+        }
       }
     }
     }
@@ -692,7 +714,7 @@ extern "C" long long bd_attention_tc_workspace_bytes(int B, int H, int Lq, int L
 static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
                                const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
                                float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
-                               int split, void *workspace, bd_stream_t stream, int phase);
+                               int split, void *workspace, bd_stream_t stream, int phase, int io16 = 0);
 
 extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
                                const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
@@ -702,29 +724,46 @@ extern "C" int bd_attention_tc(const float *Q, int ldq, long long sq_b, const fl
                              scale, split, workspace, stream, 3);
 }
 
+// bd_attention_tc with 16-bit tensors in HBM: io_half bit 0 = Q, bit 1 = K, bit 2 = V, bit 3 = O are fp16 (their
+// leading dimensions and batch strides count halfs; rows 8-byte aligned).  Values: Q / K / V are rounded to fp16
+// inside the kernel anyway; an fp16 O is what the out-projection would round it to.
+extern "C" int bd_attention_tc_h(const void *Q, int ldq, long long sq_b, const void *K, int ldk, long long sk_b,
+                                 const void *V, int ldv, long long sv_b, const unsigned char *key_padding_mask, void *O,
+                                 int ldo, long long so_b, int io_half, int B, int H, int Lq, int Lk, int hd, float scale,
+                                 int split, void *workspace, bd_stream_t stream) {
+  BD_REQUIRE(g_attn_impl == 1, "bd_attention_tc_h: only with the warp-specialised kernel");
+  return attention_tc_phases(static_cast<const float *>(Q), ldq, sq_b, static_cast<const float *>(K), ldk, sk_b,
+                             static_cast<const float *>(V), ldv, sv_b, key_padding_mask, static_cast<float *>(O), ldo, so_b, B,
+                             H, Lq, Lk, hd, scale, split, workspace, stream, 3, io_half & 15);
+}
+
 // The two halves of bd_attention_tc for keys / values that are known long before their queries (the
 // decoder's memory K / V): pack once, on another stream, off the critical path; attend later.  Same Lq,
 // Lk, split and workspace in both calls (the workspace layout depends on them).
-extern "C" int bd_attention_tc_pack_kv(const float *K, int ldk, long long sk_b, const float *V, int ldv, long long sv_b,
-                                       int B, int H, int Lq, int Lk, int hd, int split, void *workspace,
+extern "C" int bd_attention_tc_pack_kv(const void *K, int ldk, long long sk_b, const void *V, int ldv, long long sv_b,
+                                       int kv_half, int B, int H, int Lq, int Lk, int hd, int split, void *workspace,
                                        bd_stream_t stream) {
   BD_REQUIRE(g_attn_impl == 1, "bd_attention_tc_pack_kv: only with the warp-specialised kernel");
-  return attention_tc_phases(K, 4, 0, K, ldk, sk_b, V, ldv, sv_b, nullptr, reinterpret_cast<float *>(workspace), 4, 0, B, H,
-                             Lq, Lk, hd, 1.0f, split, workspace, stream, 1);
+  return attention_tc_phases(static_cast<const float *>(K), 4, 0, static_cast<const float *>(K), ldk, sk_b,
+                             static_cast<const float *>(V), ldv, sv_b, nullptr, reinterpret_cast<float *>(workspace), 4, 0, B, H,
+                             Lq, Lk, hd, 1.0f, split, workspace, stream, 1, kv_half ? 6 : 0);
 }
-extern "C" int bd_attention_tc_packed(const float *Q, int ldq, long long sq_b, const unsigned char *key_padding_mask,
-                                      float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd,
+extern "C" int bd_attention_tc_packed(const void *Q, int ldq, long long sq_b, const unsigned char *key_padding_mask,
+                                      void *O, int ldo, long long so_b, int io_half, int B, int H, int Lq, int Lk, int hd,
                                       float scale, int split, void *workspace, bd_stream_t stream) {
   BD_REQUIRE(g_attn_impl == 1, "bd_attention_tc_packed: only with the warp-specialised kernel");
-  return attention_tc_phases(Q, ldq, sq_b, Q, 4, 0, Q, 4, 0, key_padding_mask, O, ldo, so_b, B, H, Lq, Lk, hd, scale, split,
-                             workspace, stream, 2);
+  return attention_tc_phases(static_cast<const float *>(Q), ldq, sq_b, static_cast<const float *>(Q), 4, 0,
+                             static_cast<const float *>(Q), 4, 0, key_padding_mask, static_cast<float *>(O), ldo, so_b, B, H,
+                             Lq, Lk, hd, scale, split, workspace, stream, 2, io_half & 9);
 }
 
 static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
                                const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
                                float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
-                               int split, void *workspace, bd_stream_t stream, int phase) {
+                               int split, void *workspace, bd_stream_t stream, int phase, int io16) {
   BD_REQUIRE(Q && K && V && O && workspace, "bd_attention_tc: null pointer");
+  BD_REQUIRE(io16 == 0 || (g_attn_impl == 1 && ldv % 4 == 0 && sv_b % 4 == 0 && (reinterpret_cast<uintptr_t>(V) & 7) == 0),
+             "bd_attention_tc: fp16 tensors need the warp-specialised kernel and 8-byte aligned rows");
   BD_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && B <= 65535 && H <= 65535, "bd_attention_tc: bad sizes");
   BD_REQUIRE(hd == AT_HD, "bd_attention_tc: built for head_dim 36 (d_model 288 / 8 heads)");
   BD_REQUIRE(split == 1 || split == 3, "bd_attention_tc: split must be 1 (bf16) or 3 (bf16x3)");
@@ -743,6 +782,7 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
   p.Lq = Lq, p.Lk = Lk, p.H = H;
   p.nq = bd::ceil_div(Lq, AT_BM), p.nk = bd::ceil_div(Lk, BK);
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.q16 = io16 & 1, p.k16 = (io16 >> 1) & 1, p.v16 = (io16 >> 2) & 1, p.o16 = (io16 >> 3) & 1;
   p.dbg = g_attn_dbg;
   const size_t parts = split == 3 ? 2 : 1;
   unsigned char *ws = static_cast<unsigned char *>(workspace);

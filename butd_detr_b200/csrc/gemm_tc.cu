@@ -48,6 +48,12 @@ struct LinearTcParams {
   int g_ldf, g_ldx, g_C, g_ns, g_n, g_m;
   float g_inv_r;
   int pool;  // > 0: max over groups of `pool` consecutive rows in the epilogue (F.max_pool2d over nsample)
+  // 16-bit activations in HBM (fp16 mode, plain A): a16 = A is an fp16 (M, K) matrix and arrives by ONE tensor
+  // copy per chunk directly in the swizzled operand layout (no conversion pass, half the bytes); y16 = the
+  // plain epilogue writes fp16 rows to Y16 INSTEAD of fp32 rows to Y; the LayerNorm epilogue writes its fp32
+  // rows AND, when Y16 is set, an fp16 copy (the operand of the next projection)
+  int a16, y16, ldy16;
+  __half *Y16;
   long long *dbg;  // optional clock64() stamps of CTA (0,0), thread 0 (tuning aid)
 };
 
@@ -86,7 +92,8 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   // variant stages through registers (LSU)
   constexpr bool TMA_A = MODE == 0 || (MODE == 1 && EPI != 1);  // (LayerNorm + A2: full-row weights leave no room)
   constexpr uint32_t RAW = 2 * A_PART;  // one raw fp32 chunk: 128 rows x 256 B
-  const uint32_t a_bytes = TMA_A ? (HAS_A2 ? 2 * RAW : RAW) : A_PART * parts, w_bytes = w_blk * parts * n_sub;
+  const bool A16 = MODE == 0 && p.a16;  // fp16 activations: the tensor copy delivers the operand tile itself
+  const uint32_t a_bytes = A16 ? A_PART : (TMA_A ? (HAS_A2 ? 2 * RAW : RAW) : A_PART * parts), w_bytes = w_blk * parts * n_sub;
   const uint32_t stage_bytes = a_bytes + w_bytes;
   const uint32_t ncols = tc::tmem_cols_pow2(n_sub * BN);
 
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
       const uint32_t par = (c / S) & 1;
       tc::mbar_wait(tc::smem_u32(&bar_w[st]), par);
       TC_STAMP_T(10 + 3 * c, TC_WARPS * 32);
-      tc::mbar_wait(tc::smem_u32(&bar_a[st]), par);
+      tc::mbar_wait(tc::smem_u32(A16 ? &bar_raw[st] : &bar_a[st]), par);  // fp16 A: straight from the tensor copy
       TC_STAMP_T(11 + 3 * c, TC_WARPS * 32);
       tc::fence_after_sync();
       if (tc::elect_one()) {
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
           // one tensor copy per chunk: box (64 k x 128 rows) at (c * 64, row0); rows >= M and k >= K
           // are zero-filled by the TMA unit and still count towards the full 32 KB
           const uint32_t bar = tc::smem_u32(&bar_raw[st]);
-          tc::mbar_arrive_expect_tx(bar, HAS_A2 ? 2 * RAW : RAW);
+          tc::mbar_arrive_expect_tx(bar, A16 ? A_PART : (HAS_A2 ? 2 * RAW : RAW));
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                   tc::smem_u32(smem + st * stage_bytes)),
@@ -335,7 +342,9 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_a[st]));
       TC_STAMP(4 + c);
     };
-    if (TMA_A) {
+    if (A16) {
+      // nothing to stage: the MMA warp consumes the tensor copies directly
+    } else if (TMA_A) {
       for (int c = 0; c < p.n_chunks; ++c) step_tma(c);
     } else {
       for (int c = 0; c < p.n_chunks; c += 2) {
@@ -412,6 +421,12 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
             if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
             o[j] = v;
           }
+          if (EPI == 0 && p.y16) {  // fp16 rows: row stride NC + 8 halfs
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(tile) + r * (NC + 8) + (g + u) * 16);
+            dst[0] = make_uint4(tc::pack_f16x2(o[0], o[1]), tc::pack_f16x2(o[2], o[3]), tc::pack_f16x2(o[4], o[5]), tc::pack_f16x2(o[6], o[7]));
+            dst[1] = make_uint4(tc::pack_f16x2(o[8], o[9]), tc::pack_f16x2(o[10], o[11]), tc::pack_f16x2(o[12], o[13]), tc::pack_f16x2(o[14], o[15]));
+            continue;
+          }
           float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + (g + u) * 16);
           dst[0] = make_float4(o[0], o[1], o[2], o[3]);
           dst[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -436,6 +451,26 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
         float mx = t[0];
         for (int q = 1; q < p.pool; ++q) mx = fmaxf(mx, t[q * ldt]);
         p.Y[orow * p.ldy + col_base + col] = mx;
+      }
+    } else if (EPI == 0 && p.y16) {
+      // fp16 rows (ldy16 % 8 == 0, 16-byte aligned Y16: checked by the host wrapper)
+      const __half *t16 = reinterpret_cast<const __half *>(tile);
+      if (n_valid % 8 == 0 && col_base % 8 == 0) {
+        if (tid < TC_BM && row0 + tid < p.M) {
+          __half *y = p.Y16 + static_cast<long long>(row0 + tid) * p.ldy16 + col_base;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y),
+                       "r"(tc::smem_u32(t16 + tid * (NC + 8))), "r"(n_valid * 2)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      } else {
+        for (int r = warp; r < TC_BM; r += TC_WARPS) {
+          const int gr = row0 + r;
+          if (gr >= p.M) break;
+          __half *y = p.Y16 + static_cast<long long>(gr) * p.ldy16 + col_base;
+          for (int q = lane; q < n_valid; q += 32) y[q] = t16[r * (NC + 8) + q];
+        }
       }
     } else if (EPI == 0) {
       const bool vec = (p.ldy % 4 == 0) && (n_valid % 4 == 0) && (col_base % 4 == 0) &&
@@ -500,9 +535,14 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
 #pragma unroll
           for (int i = 0; i < LN_V; ++i) {
             const int v = lane + i * 32;
-            if (v < nv)
-              y[v] = make_float4((x[u][i].x - mean) * rstd * gam[i].x + bet[i].x, (x[u][i].y - mean) * rstd * gam[i].y + bet[i].y,
-                                 (x[u][i].z - mean) * rstd * gam[i].z + bet[i].z, (x[u][i].w - mean) * rstd * gam[i].w + bet[i].w);
+            if (v < nv) {
+              const float4 o4 = make_float4((x[u][i].x - mean) * rstd * gam[i].x + bet[i].x, (x[u][i].y - mean) * rstd * gam[i].y + bet[i].y,
+                                            (x[u][i].z - mean) * rstd * gam[i].z + bet[i].z, (x[u][i].w - mean) * rstd * gam[i].w + bet[i].w);
+              y[v] = o4;
+              if (p.Y16)  // fp16 copy: the A operand of the projections that read this row next
+                reinterpret_cast<uint2 *>(p.Y16 + static_cast<long long>(gr) * p.ldy16)[v] =
+                    make_uint2(tc::pack_f16x2(o4.x, o4.y), tc::pack_f16x2(o4.z, o4.w));
+            }
           }
         }
       };
@@ -544,6 +584,14 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
     BD_REQUIRE(enc != nullptr, "bd_linear_tc: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.K), static_cast<cuuint64_t>(p.M)};
     const cuuint32_t box[2] = {KC, TC_BM}, estr[2] = {1, 1};
+    if (p.a16) {  // fp16 rows, 128-byte swizzle: the copy lands in the MMA operand layout
+      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.lda) * sizeof(__half)};
+      const CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<float *>(p.A), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      BD_REQUIRE(r == CUDA_SUCCESS, "bd_linear_tc: cuTensorMapEncodeTiled (fp16) failed (%d) for M=%d K=%d ld=%d",
+                 static_cast<int>(r), p.M, p.K, p.lda);
+    } else
     for (int which = 0; which < (p.A2 ? 2 : 1); ++which) {
       const cuuint64_t strides[1] = {static_cast<cuuint64_t>(which ? p.lda2 : p.lda) * sizeof(float)};
       const CUresult r = enc(which ? &p.tmA2 : &p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
@@ -557,7 +605,7 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   const uint32_t parts = p.split == 3 ? 2 : 1;
   // the A region of a stage holds the raw fp32 chunk(s) first: 32 KB, 64 KB with A2; gather: the operand only
   const bool lsu_a = p.g_idx || (ln && p.A2);
-  const size_t a_region = lsu_a ? parts * A_PART : (p.A2 ? 4 * A_PART : 2 * A_PART);
+  const size_t a_region = p.a16 ? A_PART : (lsu_a ? parts * A_PART : (p.A2 ? 4 * A_PART : 2 * A_PART));
   const size_t stage = a_region + static_cast<size_t>(parts) * NC * KC * 2;
   int stages = static_cast<int>((217 * 1024) / stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -678,6 +726,59 @@ extern "C" int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda
   const int r2 = launch_linear_tc(p, true, bd::as_stream(stream));
   if (r2 != BD_OK) return r2;
   BD_CHECK_LAUNCH("bd_linear_ln_tc");
+  return BD_OK;
+}
+
+// 16-bit activation variants (fp16 operand mode only, split = 1, no A2).  a_half: A is an fp16 (M, K) matrix
+// (lda in halfs, lda % 8 == 0); y_half: Y is written as fp16 rows (ldy in halfs, ldy % 8 == 0).  Values are the
+// ones the fp32 entry points produce followed by the fp16 rounding their consumers apply anyway.
+extern "C" int bd_linear_tc_h(const void *A, int lda, int a_half, const float *A2, int lda2, const void *Wp,
+                              const float *bias, void *Y, int ldy, int y_half, int M, int N, int K, int kc, int n_chunks,
+                              int BN, int n_sub, int relu, bd_stream_t stream) {
+  BD_REQUIRE(A && Wp && Y, "bd_linear_tc_h: null pointer");
+  BD_REQUIRE(!A2 || (!a_half && lda2 >= K && lda2 % 4 == 0 && (reinterpret_cast<uintptr_t>(A2) & 15) == 0),
+             "bd_linear_tc_h: A2 (fp32, 16-byte aligned rows) only with an fp32 A");
+  BD_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldy >= N, "bd_linear_tc_h: bad sizes");
+  BD_REQUIRE(kc == KC && n_chunks >= 1 && n_chunks * KC >= K && K % 8 == 0, "bd_linear_tc_h: KC must be 64, K %% 8 == 0");
+  BD_REQUIRE(lda % (a_half ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, "bd_linear_tc_h: A rows must be 16-byte aligned");
+  BD_REQUIRE(!y_half || (ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0), "bd_linear_tc_h: fp16 Y rows must be 16-byte aligned");
+  BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && n_sub >= 1 && n_sub * BN <= 512, "bd_linear_tc_h: bad tiling");
+  LinearTcParams p = {};
+  p.A = static_cast<const float *>(A), p.A2 = A2, p.lda2 = lda2, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp);
+  p.Y = static_cast<float *>(Y), p.Y16 = static_cast<__half *>(Y), p.lda = lda, p.ldy = ldy, p.ldy16 = ldy;
+  p.a16 = a_half ? 1 : 0, p.y16 = y_half ? 1 : 0;
+  p.M = M, p.N = N, p.K = K, p.n_chunks = n_chunks, p.BN = BN, p.n_sub = n_sub, p.relu = relu, p.split = 1;
+  p.dbg = g_tc_dbg;
+  const int r2 = launch_linear_tc(p, false, bd::as_stream(stream));
+  if (r2 != BD_OK) return r2;
+  BD_CHECK_LAUNCH("bd_linear_tc_h");
+  return BD_OK;
+}
+
+extern "C" int bd_linear_ln_tc_h(const void *A, int lda, int a_half, const void *Wp, const float *bias, const float *R,
+                                 int ldr, const float *gamma, const float *beta, float eps, float *Y, int ldy, void *Y16,
+                                 int ldy16, int M, int N, int K, int kc, int n_chunks, int BN, int n_sub,
+                                 bd_stream_t stream) {
+  BD_REQUIRE(A && Wp && Y && R && gamma && beta, "bd_linear_ln_tc_h: null pointer");
+  BD_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldy >= N && ldr >= N, "bd_linear_ln_tc_h: bad sizes");
+  BD_REQUIRE(kc == KC && n_chunks >= 1 && n_chunks * KC >= K && K % 8 == 0, "bd_linear_ln_tc_h: KC must be 64, K %% 8 == 0");
+  BD_REQUIRE(lda % (a_half ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, "bd_linear_ln_tc_h: A rows must be 16-byte aligned");
+  BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && n_sub >= 1 && n_sub * BN <= 512, "bd_linear_ln_tc_h: bad tiling");
+  BD_REQUIRE(n_sub * BN >= N && N <= 320, "bd_linear_ln_tc_h: one CTA must own complete rows (N <= n_sub*BN, N <= 320)");
+  BD_REQUIRE(N % 4 == 0 && ldr % 4 == 0 && ldy % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(gamma) |
+                   reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+             "bd_linear_ln_tc_h: N, ldr, ldy must be multiples of 4 and R, Y, gamma, beta 16-byte aligned");
+  BD_REQUIRE(!Y16 || (ldy16 % 4 == 0 && ldy16 >= N && (reinterpret_cast<uintptr_t>(Y16) & 7) == 0), "bd_linear_ln_tc_h: bad Y16");
+  LinearTcParams p = {};
+  p.A = static_cast<const float *>(A), p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y;
+  p.R = R, p.gamma = gamma, p.beta = beta, p.eps = eps, p.ldr = ldr;
+  p.lda = lda, p.ldy = ldy, p.a16 = a_half ? 1 : 0, p.Y16 = static_cast<__half *>(Y16), p.ldy16 = ldy16;
+  p.M = M, p.N = N, p.K = K, p.n_chunks = n_chunks, p.BN = BN, p.n_sub = n_sub, p.relu = 0, p.split = 1;
+  p.dbg = g_tc_dbg;
+  const int r2 = launch_linear_tc(p, true, bd::as_stream(stream));
+  if (r2 != BD_OK) return r2;
+  BD_CHECK_LAUNCH("bd_linear_ln_tc_h");
   return BD_OK;
 }
 

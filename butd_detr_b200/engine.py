@@ -91,6 +91,10 @@ FPS_GRID_MIN_BATCH = 38  # scenes from which SA1's FPS runs as the bucketed one-
 DECODER_SPLIT_MIN = int(__import__("os").environ.get("BUTD_DECODER_SPLIT_MIN", 1 << 30))  # scenes per half above which the decoder would run as two batch halves on two streams:
 # measured at 32 scenes: 2336 vs 2400 scenes/s — no gain (the kernels of one half already fill a wave), so it is off
 FUSED_SA = True  # set-abstraction levels as one kernel (bd_sa_mlp_tc); False = three GEMM launches
+HALF_ACT = True  # fp16 mode: activations that are only ever GEMM operands (FFN / head / objectness hidden layers) live
+# in HBM as fp16, and every LayerNorm output gets an fp16 copy that the next projections read by tensor copy straight
+# into the operand layout (bd_linear_tc_h / bd_linear_ln_tc_h) — the values are the ones the fp32 path rounds to fp16
+# inside the consumer anyway, the bytes are half
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
 
@@ -267,6 +271,8 @@ class ForwardEngine:
             raise ValueError("precision must be 'fp32' (SIMT), 'fp16' (tcgen05, fp16 operands, one MMA per product) "
                              "or 'bf16x3' (tcgen05, bf16 hi/lo split operands, three MMAs per product)")
         self.split = 3 if self.precision == "bf16x3" else 1
+        self.half = self.precision == "fp16" and HALF_ACT
+        self._shadow = {}  # data_ptr of an fp32 LayerNorm output -> its fp16 copy (this forward)
         self._tc = {}  # key -> (packed bf16 weight, (BN, KC, n_chunks)), built on first use
         self.d_model = cfg["d_model"]
         self.n_heads = 8
@@ -289,11 +295,33 @@ class ForwardEngine:
         self._live.append(t)
         return t
 
-    def lin(self, x, key, relu=False, add=None, out=None):
+    def lin(self, x, key, relu=False, add=None, out=None, half_out=False):
         W, b = self.W[key]
         M, K = x.shape
         N = W.shape[0]
         assert x.stride(1) == 1 and W.shape[1] == K, (key, x.shape, W.shape)
+        # 16-bit activations (fp16 mode): an fp16 input, or the fp16 copy of an fp32 LayerNorm output
+        a_half = x.dtype == torch.float16
+        if self.half and add is None and not a_half and x.is_contiguous():
+            sh = self._shadow.get(x.data_ptr())
+            if sh is not None and sh.shape == x.shape:
+                x, a_half = sh, True
+        assert not (a_half and add is not None), key
+        y_half = bool(half_out and self.half and out is None)
+        if (a_half or y_half) and K % 8 == 0 and x.stride(0) % (8 if a_half else 4) == 0 and x.data_ptr() % 16 == 0 and \
+                (add is None or (add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0)):
+            wide, bn = lin_tiling(M, N)
+            tkey = f"{key}#{'wide' if wide else bn}"
+            if tkey not in self._tc:
+                self._tc[tkey] = pack_weight_tc(W, self.split, wide=wide, bn=bn)
+            Wp, (BN, KC, n_chunks, n_sub) = self._tc[tkey]
+            if out is None:
+                out = self._empty(M, _round_up(N, 8), dtype=torch.float16)[:, :N] if y_half else self._empty(M, N)
+            _lib.call("bd_linear_tc_h", x.data_ptr(), x.stride(0), int(a_half), _lib.ptr(add),
+                      0 if add is None else add.stride(0), Wp.data_ptr(), _lib.ptr(b), out.data_ptr(),
+                      out.stride(0), int(y_half), M, N, K, KC, n_chunks, BN, n_sub, int(relu))
+            return out
+        assert not a_half, key
         if out is None:
             out = self._empty(M, N)
         assert out.stride(1) == 1
@@ -317,11 +345,29 @@ class ForwardEngine:
                       out.data_ptr(), out.stride(0), M, N, K, int(relu))
         return out
 
-    def lin_ln(self, x, key, res, ln_key, add=None, eps=LN_EPS):
-        """LayerNorm(res + linear(x [+ add])) — one kernel on the tensor-core path."""
+    def lin_ln(self, x, key, res, ln_key, add=None, eps=LN_EPS, shadow=True):
+        """LayerNorm(res + linear(x [+ add])) — one kernel on the tensor-core path.  fp16 mode: also writes
+        the fp16 copy of the result (`shadow`) that the next projections read as their operand."""
         W, b = self.W[key]
         M, K = x.shape
         N = W.shape[0]
+        if self.half and add is None and N <= 320 and N % 4 == 0 and K % 8 == 0 and x.data_ptr() % 16 == 0 and \
+                x.stride(0) % (8 if x.dtype == torch.float16 else 4) == 0:
+            assert x.stride(1) == 1 and W.shape[1] == K and res.is_contiguous() and res.shape == (M, N)
+            tkey = key + "#rows"
+            if tkey not in self._tc:
+                self._tc[tkey] = pack_weight_tc(W, self.split, full_rows=True)
+            Wp, (BN, KC, n_chunks, n_sub) = self._tc[tkey]
+            g, beta = self.W[ln_key]
+            out = self._empty(M, N)
+            sh = self._empty(M, N, dtype=torch.float16) if shadow else None
+            _lib.call("bd_linear_ln_tc_h", x.data_ptr(), x.stride(0), int(x.dtype == torch.float16), Wp.data_ptr(),
+                      _lib.ptr(b), res.data_ptr(), N, g.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), N,
+                      _lib.ptr(sh), N, M, N, K, KC, n_chunks, BN, n_sub)
+            if sh is not None:
+                self._shadow[out.data_ptr()] = sh
+            return out
+        assert x.dtype == torch.float32, key
         if (self.precision == "fp32" or N > 320 or N % 4 or K % 8 or x.stride(0) % 4 or x.data_ptr() % 16 or
                 (add is not None and (add.stride(0) % 4 or add.data_ptr() % 16))):
             return self.add_ln(self.lin(x, key, add=add), res, ln_key, eps)
@@ -351,12 +397,23 @@ class ForwardEngine:
         """q (B*Lq, >=E) / k, v (B*Lk, >=E) 2-D views (row stride = leading dim) -> (B*Lq, E)."""
         E, H = self.d_model, self.n_heads
         hd = E // H
+        aligned = (hd == 36 and q.stride(0) % 4 == 0 and k.stride(0) % 4 == 0 and q.data_ptr() % 16 == 0
+                   and k.data_ptr() % 16 == 0)
+        if self.half and aligned and v.stride(0) % 4 == 0 and v.data_ptr() % 8 == 0:
+            # 16-bit tensors in HBM: fp16 q / k / v where the projections wrote them so, fp16 output (the
+            # out-projection's operand)
+            out = self._empty(B * Lq, E, dtype=torch.float16)
+            io = (int(q.dtype == torch.float16) | int(k.dtype == torch.float16) << 1 | int(v.dtype == torch.float16) << 2 | 8)
+            ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
+            _lib.call("bd_attention_tc_h", q.data_ptr(), q.stride(0), Lq * q.stride(0), k.data_ptr(), k.stride(0),
+                      Lk * k.stride(0), v.data_ptr(), v.stride(0), Lk * v.stride(0), _lib.ptr(mask), out.data_ptr(), E, Lq * E,
+                      io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), self.split, ws.data_ptr())
+            return out
+        assert q.dtype == k.dtype == v.dtype == torch.float32
         out = self._empty(B * Lq, E)
         args = (q.data_ptr(), q.stride(0), Lq * q.stride(0), k.data_ptr(), k.stride(0), Lk * k.stride(0),
                 v.data_ptr(), v.stride(0), Lk * v.stride(0), _lib.ptr(mask), out.data_ptr(), E, Lq * E, B, H, Lq, Lk,
                 hd, 1.0 / math.sqrt(hd))
-        aligned = (hd == 36 and q.stride(0) % 4 == 0 and k.stride(0) % 4 == 0 and q.data_ptr() % 16 == 0
-                   and k.data_ptr() % 16 == 0)
         if self.precision != "fp32" and aligned:
             ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
             _lib.call("bd_attention_tc", *args, self.split, ws.data_ptr())
@@ -375,16 +432,17 @@ class ForwardEngine:
             return None
         ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
         _lib.call("bd_attention_tc_pack_kv", k.data_ptr(), k.stride(0), Lk * k.stride(0), v.data_ptr(), v.stride(0),
-                  Lk * v.stride(0), B, H, Lq, Lk, hd, self.split, ws.data_ptr())
+                  Lk * v.stride(0), int(kv.dtype == torch.float16), B, H, Lq, Lk, hd, self.split, ws.data_ptr())
         return ws
 
     def attention_packed(self, q, ws, B, Lq, Lk, mask):
         """attention() over K / V tiles packed by pack_kv (same B, Lq, Lk)."""
         E, H = self.d_model, self.n_heads
         hd = E // H
-        out = self._empty(B * Lq, E)
+        out = self._empty(B * Lq, E, dtype=torch.float16 if self.half else torch.float32)
+        io = int(q.dtype == torch.float16) | (8 if self.half else 0)
         _lib.call("bd_attention_tc_packed", q.data_ptr(), q.stride(0), Lq * q.stride(0), _lib.ptr(mask), out.data_ptr(), E,
-                  Lq * E, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), self.split, ws.data_ptr())
+                  Lq * E, io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), self.split, ws.data_ptr())
         return out
 
     def mha(self, key, x_q, pos_q, x_kv, pos_k, B, Lq, Lk, mask, self_attn=False, res=None, ln_key=None, kv=None,
@@ -394,33 +452,33 @@ class ForwardEngine:
         post-LN residual block every call site of the reference wraps around the attention."""
         E = self.d_model
         if self_attn and pos_q is None:  # q = k = v = x : one fused QKV GEMM
-            qkv = self.lin(x_q, key + ".qkv")
+            qkv = self.lin(x_q, key + ".qkv", half_out=True)
             q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
         elif self_attn:  # q = k = x + pos, v = x : the V projection runs beside the Q/K one
             cur = torch.cuda.current_stream()
             aux = self.aux_stream
             aux.wait_event(cur.record_event())
             with torch.cuda.stream(aux):
-                v = self.lin(x_q, key + ".v")
+                v = self.lin(x_q, key + ".v", half_out=True)
                 v_ready = aux.record_event()
-            qk = self.lin(x_q, key + ".qk", add=pos_q)
+            qk = self.lin(x_q, key + ".qk", add=pos_q, half_out=True)
             q, k = qk[:, :E], qk[:, E:]
             cur.wait_event(v_ready)
         else:  # cross attention: k = v = memory (no positional term in this model)
-            q = self.lin(x_q, key + ".q", add=pos_q)
+            q = self.lin(x_q, key + ".q", add=pos_q, half_out=True)
             assert pos_k is None
             if packed is not None and q.stride(0) % 4 == 0 and q.data_ptr() % 16 == 0:
                 # memory K / V projected AND packed earlier on kv_stream
                 return self.lin_ln(self.attention_packed(q, packed, B, Lq, Lk, mask), key + ".o", res, ln_key)
             if kv is None:  # else: projected earlier on kv_stream
-                kv = self.lin(x_kv, key + ".kv")
+                kv = self.lin(x_kv, key + ".kv", half_out=True)
             k, v = kv[:, :E], kv[:, E:]
         o = self.attention(q, k, v, B, Lq, Lk, mask)
         return self.lin_ln(o, key + ".o", res, ln_key)
 
     def ffn(self, x, key, ln_key):
         """LayerNorm(x + W2 relu(W1 x))  (encoder_decoder_layers.py:52-58,96,122)."""
-        return self.lin_ln(self.lin(x, key + ".0", relu=True), key + ".1", x, ln_key)
+        return self.lin_ln(self.lin(x, key + ".0", relu=True, half_out=True), key + ".1", x, ln_key)
 
     def posembed(self, x, key):
         return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
@@ -430,19 +488,19 @@ class ForwardEngine:
         `out`: dict of row views {center (n,3), size (n,3), sem (n,C)} of the full-batch outputs.
         Class scores run on head_stream: nothing downstream on the calling stream needs them."""
         E = self.d_model
-        stem = self.lin(feats, key + ".stem", relu=True)  # (n, 3E)
+        stem = self.lin(feats, key + ".stem", relu=True, half_out=True)  # (n, 3E)
         cur = torch.cuda.current_stream()
         self.head_stream.wait_event(cur.record_event())
         with torch.cuda.stream(self.head_stream):
-            h = self.lin(stem[:, 2 * E:3 * E], f"{key}.sem.1", relu=True)
+            h = self.lin(stem[:, 2 * E:3 * E], f"{key}.sem.1", relu=True, half_out=True)
             self.lin(h, f"{key}.sem.2", out=out["sem"])
         aux = self.aux_stream
         aux.wait_event(cur.record_event())
         with torch.cuda.stream(aux):  # the size branch beside the centre branch
-            h2 = self.lin(stem[:, E:2 * E], f"{key}.size.1", relu=True)
+            h2 = self.lin(stem[:, E:2 * E], f"{key}.size.1", relu=True, half_out=True)
             self.lin(h2, f"{key}.size.2", out=out["size"])
             size_ready = aux.record_event()
-        h = self.lin(stem[:, :E], f"{key}.center.1", relu=True)
+        h = self.lin(stem[:, :E], f"{key}.center.1", relu=True, half_out=True)
         delta = self.lin(h, f"{key}.center.2")
         n = feats.shape[0]
         _lib.call("bd_add_rows", base_xyz.data_ptr(), 3, delta.data_ptr(), 3, out["center"].data_ptr(), 3, n, 3)
@@ -450,8 +508,8 @@ class ForwardEngine:
         return out["center"], out["size"]
 
     def contrastive(self, x, side, B, L, out=None):
-        h = self.lin(x, f"contrastive.{side}.0", relu=True)
-        h = self.lin(h, f"contrastive.{side}.1", relu=True)
+        h = self.lin(x, f"contrastive.{side}.0", relu=True, half_out=True)
+        h = self.lin(h, f"contrastive.{side}.1", relu=True, half_out=True)
         h = self.lin(h, f"contrastive.{side}.2", out=out)
         _lib.call("bd_l2_normalize_rows", h.data_ptr(), h.data_ptr(), h.shape[0], h.shape[1])
         return h.view(B, L, -1)
@@ -700,6 +758,7 @@ class ForwardEngine:
         B = inputs["text_hidden"].shape[0]
         ep = {}
         self._live = []
+        self._shadow = {}
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
             if "seed" in ov:  # backbone output supplied: (B,V,E) token-major features, (B,V,3), (B,V) i32
@@ -770,9 +829,9 @@ class ForwardEngine:
             with torch.cuda.stream(kvs):
                 for i in range(cfg["num_decoder_layers"]):
                     k = f"dec{i}"
-                    kv_l = self.lin(text, k + ".l.kv")
-                    kv_d = self.lin(det, k + ".d.kv") if cfg["butd"] else None
-                    kv_v = self.lin(vis, k + ".v.kv")
+                    kv_l = self.lin(text, k + ".l.kv", half_out=True)
+                    kv_d = self.lin(det, k + ".d.kv", half_out=True) if cfg["butd"] else None
+                    kv_v = self.lin(vis, k + ".v.kv", half_out=True)
                     # ... and their K / V^T operand tiles: the decoder's attention calls then start at the
                     # attention kernel itself (whole batch only: the tile image is not sliceable by scene)
                     Qn = cfg["num_queries"]
@@ -789,8 +848,8 @@ class ForwardEngine:
                     ep["proj_tokens"] = self.contrastive(text, "text", B, L)
             # ---- query generation (models/bdetr.py:177-191)
             torch.cuda.nvtx.range_push("butd/query_generation") if NVTX else None
-            h = self.lin(vis, "points_obj_cls.conv1", relu=True)
-            h = self.lin(h, "points_obj_cls.conv2", relu=True)
+            h = self.lin(vis, "points_obj_cls.conv1", relu=True, half_out=True)
+            h = self.lin(h, "points_obj_cls.conv2", relu=True, half_out=True)
             logits = self.lin(h, "points_obj_cls.conv3")  # (B*V, 1)
             ep["seeds_obj_cls_logits"] = logits.view(B, V, 1).transpose(1, 2)
             Q = cfg["num_queries"]

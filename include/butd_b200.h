@@ -208,6 +208,20 @@ int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, int C, const 
                  const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
                  const float *b2, int N2, float *Y, int ldy, int split, bd_stream_t stream);
 
+/* 16-bit activation variants of bd_linear_tc / bd_linear_ln_tc (fp16 operand mode; an fp32 A2 may be
+ * added to an fp32 A as in bd_linear_tc): a_half = A
+ * is an fp16 (M, K) matrix (lda in halfs, % 8) that arrives by tensor copy directly in the swizzled
+ * operand layout — no conversion pass, half the bytes; y_half = Y is written as fp16 rows (ldy in
+ * halfs, % 8).  bd_linear_ln_tc_h always writes its fp32 rows (the residual stream) and, when Y16 is
+ * not NULL, an fp16 copy for the projections that consume the rows next.  Values equal the fp32
+ * entry points' followed by the fp16 rounding their consumers apply anyway. */
+int bd_linear_tc_h(const void *A, int lda, int a_half, const float *A2, int lda2, const void *Wp,
+                   const float *bias, void *Y, int ldy, int y_half, int M, int N, int K, int kc,
+                   int n_chunks, int BN, int n_sub, int relu, bd_stream_t stream);
+int bd_linear_ln_tc_h(const void *A, int lda, int a_half, const void *Wp, const float *bias,
+                      const float *R, int ldr, const float *gamma, const float *beta, float eps,
+                      float *Y, int ldy, void *Y16, int ldy16, int M, int N, int K, int kc,
+                      int n_chunks, int BN, int n_sub, bd_stream_t stream);
 /* Occupancy policy of bd_linear_tc / bd_linear_pool_tc: 1 (default) = two CTAs per SM where the
  * accumulators fit 256 TMEM columns and the grid exceeds one wave; 0 = one CTA per SM, deepest ring. */
 int bd_linear_tc_set_occupancy(int two_per_sm);
@@ -264,13 +278,21 @@ int bd_attention_tc_select(int impl);
  * decoder's memory K / V): bd_attention_tc_pack_kv writes the K / V^T operand tiles into `workspace`
  * (any stream, any time after K / V are complete), bd_attention_tc_packed attends over them.  Same
  * B, H, Lq, Lk, split and workspace in both calls. */
-int bd_attention_tc_pack_kv(const float *K, int ldk, long long sk_b, const float *V, int ldv,
-                            long long sv_b, int B, int H, int Lq, int Lk, int hd, int split,
-                            void *workspace, bd_stream_t stream);
-int bd_attention_tc_packed(const float *Q, int ldq, long long sq_b,
-                           const unsigned char *key_padding_mask, float *O, int ldo, long long so_b,
-                           int B, int H, int Lq, int Lk, int hd, float scale, int split,
+int bd_attention_tc_pack_kv(const void *K, int ldk, long long sk_b, const void *V, int ldv,
+                            long long sv_b, int kv_half, int B, int H, int Lq, int Lk, int hd,
+                            int split, void *workspace, bd_stream_t stream);
+int bd_attention_tc_packed(const void *Q, int ldq, long long sq_b,
+                           const unsigned char *key_padding_mask, void *O, int ldo, long long so_b,
+                           int io_half, int B, int H, int Lq, int Lk, int hd, float scale, int split,
                            void *workspace, bd_stream_t stream);
+/* bd_attention_tc with 16-bit tensors in HBM: io_half bit 0 = Q, bit 1 = K, bit 2 = V, bit 3 = O are
+ * fp16 (leading dimensions / batch strides in halfs, rows 8-byte aligned; kv_half of
+ * bd_attention_tc_pack_kv = both K and V; bd_attention_tc_packed reads bits 0 and 3). */
+int bd_attention_tc_h(const void *Q, int ldq, long long sq_b, const void *K, int ldk, long long sk_b,
+                      const void *V, int ldv, long long sv_b,
+                      const unsigned char *key_padding_mask, void *O, int ldo, long long so_b,
+                      int io_half, int B, int H, int Lq, int Lk, int hd, float scale, int split,
+                      void *workspace, bd_stream_t stream);
 /* Tuning hook: key sequences of at most `nk` tiles of 128 keys run as one query tile per CTA with
  * two CTAs per SM (256 TMEM columns each); longer ones as two ping-ponged query tiles per CTA.
  * Default: every length in the fp16 mode (measured faster at all of the model's shapes), none in the

@@ -295,3 +295,83 @@ def test_attention_tc_tile_variants(cuda_lib, B, Lq, Lk, masked, split, small_nk
     want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
     tol = 5e-3 if split == 1 else 1e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("a_half,y_half", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K,relu", [(1024, 576, 288, False), (300, 256, 288, True), (131, 288, 256, False),
+                                         (4099, 64, 8, True), (2048, 864, 288, False), (77, 3, 288, False)])
+def test_linear_tc_half_activations(cuda_lib, M, N, K, relu, a_half, y_half):
+    """fp16 activations in HBM: A read by tensor copy straight into the operand layout, Y written as fp16
+    rows — same values as the fp32 entry point up to the output rounding."""
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(M + N + K + a_half * 2 + y_half)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 1)
+    Ain = A.half().contiguous() if a_half else A
+    ldy = (N + 7) // 8 * 8
+    Y = torch.full((M, ldy), float("nan"), device="cuda", dtype=torch.float16 if y_half else torch.float32)
+    cuda_lib.call("bd_linear_tc_h", Ain.data_ptr(), K, a_half, None, 0, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), ldy, y_half,
+                  M, N, K, KC, nch, BN, nsub, int(relu))
+    want = F.linear(A.half().double(), W.half().double(), b.double())
+    want = (want.relu() if relu else want).float()
+    tol = 2e-3 if y_half else 1e-4
+    torch.testing.assert_close(Y[:, :N].float(), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("a_half,shadow", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(1024, 288, 256), (300, 288, 288), (2048, 160, 64)])
+def test_linear_ln_tc_half_activations(cuda_lib, M, N, K, a_half, shadow):
+    from butd_detr_b200.engine import pack_weight_tc
+    g = _g(M * 5 + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g)
+    gam, bet = torch.rand(N, device="cuda", generator=g) + 0.5, torch.randn(N, device="cuda", generator=g)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 1, full_rows=True)
+    Ain = A.half().contiguous() if a_half else A
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    Y16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16) if shadow else None
+    cuda_lib.call("bd_linear_ln_tc_h", Ain.data_ptr(), K, a_half, Wp.data_ptr(), b.data_ptr(), R.data_ptr(), N,
+                  gam.data_ptr(), bet.data_ptr(), 1e-5, Y.data_ptr(), N, cuda_lib.ptr(Y16), N, M, N, K, KC, nch, BN, nsub)
+    lin = F.linear(A.half().double(), W.half().double(), b.double())
+    want = F.layer_norm(R.double() + lin, (N,), gam.double(), bet.double(), 1e-5).float()
+    torch.testing.assert_close(Y, want, rtol=2e-4, atol=2e-4)
+    if shadow:
+        assert torch.equal(Y16, Y.half())
+
+
+@pytest.mark.parametrize("io", [15, 8, 9, 6, 14])
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 1024, False), (3, 256, 132, True), (2, 80, 80, True), (1, 300, 1000, True)])
+def test_attention_tc_half_tensors(cuda_lib, B, Lq, Lk, masked, io):
+    """fp16 Q / K / V / O in HBM (io bits 0..3), fused wider buffers as in the engine."""
+    H, hd = 8, 36
+    E = H * hd
+    lib = cuda_lib.load()
+    g = _g(Lq * 13 + Lk + io)
+    q32 = torch.randn(B, Lq, E, device="cuda", generator=g)
+    kv32 = torch.randn(B, Lk, 2 * E, device="cuda", generator=g)
+    q = q32.half() if io & 1 else q32
+    kbuf = kv32.half() if io & 2 else kv32
+    vbuf = kv32.half() if io & 4 else kv32
+    k, v = kbuf[..., :E], vbuf[..., E:]
+    mask = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), generator=torch.Generator().manual_seed(Lk))
+        mask = (torch.arange(Lk)[None] >= lens[:, None]).cuda()
+    out = torch.full((B, Lq, E), float("nan"), device="cuda", dtype=torch.float16 if io & 8 else torch.float32)
+    m8 = mask.to(torch.uint8).contiguous() if masked else None
+    ws = torch.empty(lib.bd_attention_tc_workspace_bytes(B, H, Lq, Lk, 1), dtype=torch.uint8, device="cuda")
+    cuda_lib.call("bd_attention_tc_h", q.data_ptr(), E, Lq * E, k.data_ptr(), 2 * E, Lk * 2 * E, v.data_ptr(), 2 * E,
+                  Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), 1,
+                  ws.data_ptr())
+    qh = q32.reshape(B, Lq, H, hd).transpose(1, 2).double()
+    kh = kv32[..., :E].reshape(B, Lk, H, hd).transpose(1, 2).double()
+    vh = kv32[..., E:].reshape(B, Lk, H, hd).transpose(1, 2).double()
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if masked:
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    torch.testing.assert_close(out.float(), want, rtol=6e-3, atol=6e-3)
