@@ -30,6 +30,10 @@ __host__ __device__ constexpr uint32_t v_part(int BK) { return (BK / 64) * V_BLK
 __host__ __device__ constexpr uint32_t p_part(int BK) { return (BK / 64) * P_BLK; }
 
 struct AttnParams {
+  // DIRECT variant: K and V as 2-D fp16 tensors (inner = the H * 36 columns of the projection output, rows =
+  // B * Lk tokens), box = 64 columns x 128 rows, 128-byte swizzle — a K / V tile of one head arrives in the MMA
+  // operand layout straight from the rows the projection kernel wrote (no pack kernel, no workspace)
+  CUtensorMap tmK, tmV;
   const float *Q, *K, *V;
   const unsigned char *mask;
   float *O;
@@ -44,17 +48,17 @@ struct AttnParams {
 };
 
 // 8 consecutive head dims of an fp32 or fp16 row (element offset `off`; `second`: dims 4..7 are inside the head)
-__device__ __forceinline__ void load_chunk8(const float *base, long long off, bool half, bool second, float (&v)[8]) {
+__device__ __forceinline__ void load_chunk8(const float *base, long long off, bool half, bool second, float (&v)[8], bool first = true) {
   if (half) {
     const __half *s = reinterpret_cast<const __half *>(base) + off;  // 8-byte aligned (ld % 4 == 0, head offset 72 h bytes)
-    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(s));
+    const uint2 a = first ? __ldg(reinterpret_cast<const uint2 *>(s)) : make_uint2(0u, 0u);
     const uint2 b = second ? __ldg(reinterpret_cast<const uint2 *>(s + 4)) : make_uint2(0u, 0u);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&a.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&a.y));
     const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&b.x)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&b.y));
     v[0] = f0.x, v[1] = f0.y, v[2] = f1.x, v[3] = f1.y, v[4] = f2.x, v[5] = f2.y, v[6] = f3.x, v[7] = f3.y;
   } else {
     const float4 *s = reinterpret_cast<const float4 *>(base + off);
-    const float4 a = __ldg(s);
+    const float4 a = first ? __ldg(s) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 b = second ? __ldg(s + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
   }
@@ -417,17 +421,27 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long ne
   }
 }
 
-template <int PARTS, int TILES>
-__global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES == 2 ? 1 : 2) attention_ws_kernel(const AttnParams p) {
+// DIRECT (fp16 K / V rows in HBM, PARTS == 1): the loader fetches each head's K tile [128 keys x 64 columns]
+// and V tile [128 keys x 64 columns] with ONE tensor copy each from the projection output.  A tensor copy must
+// start on a 16-byte boundary and a head starts at byte 72 h, so odd heads start 4 columns early (SHIFT = 4):
+// the tile holds columns 36 h - SHIFT .. + 63 — the head's 36 dims at SHIFT .. SHIFT + 35, around them the
+// neighbouring heads' dims / zero fill.  Q's tile is built with zeros everywhere but at its 36 dims (same
+// SHIFT), so the foreign columns of K contribute exactly nothing, and the foreign columns of P.V are not read.  V stays in its natural [key][dim] layout: the B operand of P.V is MN-major.
+// The softmax denominator comes from a second, N = 16 MMA of P against a constant tile whose first row is ones.
+constexpr uint32_t ONES_BLK = 16 * 128;  // 16 rows x 64 keys
+template <int PARTS, int TILES, bool DIRECT = false>
+__global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES == 2 ? 1 : 2) attention_ws_kernel(const __grid_constant__ AttnParams p) {
+  static_assert(!DIRECT || (PARTS == 1 && TILES == 1), "DIRECT: fp16 operands, one query tile per CTA");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr uint32_t K_PART = k_part(WS_BK), V_PART = v_part(WS_BK);
+  constexpr uint32_t K_PART = k_part(WS_BK), V_PART = DIRECT ? WS_BK * 128u : v_part(WS_BK);
   constexpr uint32_t Q_TILE = PARTS * QK_PART, K_TILE = PARTS * K_PART, V_TILE = PARTS * V_PART;
   unsigned char *sQ = smem;                   // TILES query tiles
   unsigned char *sK = sQ + TILES * Q_TILE;    // 2 stages
   constexpr int SM0 = TILES == 2 ? 4 : 2;     // first softmax warp
   constexpr uint32_t TM_COLS = TILES == 2 ? 512 : 256, TM_O = TILES == 2 ? 256 : 128;
   unsigned char *sV = sK + 2 * K_TILE;    // 2 stages
+  unsigned char *sOnes = sV + 2 * V_TILE;  // DIRECT: [2 blocks of 64 keys][16 rows][128 B], row 0 = ones
   __shared__ __align__(8) unsigned long long bar_q, bar_kf[2], bar_ke[2], bar_vf[2], bar_ve[2], bar_s[2], bar_p[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -470,16 +484,24 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
         const uint32_t par = ((j >> 1) - 1) & 1;
         if (j >= 2) tc::mbar_wait(tc::smem_u32(&bar_ke[st]), par);
         tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_kf[st]), K_TILE);
-        tc::bulk_g2s(tc::smem_u32(sK + st * K_TILE), Kp + static_cast<size_t>(j) * K_TILE, K_TILE, tc::smem_u32(&bar_kf[st]));
+        if (DIRECT)  // rows past this scene's keys (next scene / zero fill) are masked keys; the fill counts as bytes
+          tc::tma_load_2d(tc::smem_u32(sK + st * K_TILE), &p.tmK, h * AT_HD - (h & 1) * 4, b * p.Lk + j * WS_BK, tc::smem_u32(&bar_kf[st]));
+        else
+          tc::bulk_g2s(tc::smem_u32(sK + st * K_TILE), Kp + static_cast<size_t>(j) * K_TILE, K_TILE, tc::smem_u32(&bar_kf[st]));
         if (j >= 2) tc::mbar_wait(tc::smem_u32(&bar_ve[st]), par);
         tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_vf[st]), V_TILE);
-        tc::bulk_g2s(tc::smem_u32(sV + st * V_TILE), Vp + static_cast<size_t>(j) * V_TILE, V_TILE, tc::smem_u32(&bar_vf[st]));
+        if (DIRECT)
+          tc::tma_load_2d(tc::smem_u32(sV + st * V_TILE), &p.tmV, h * AT_HD - (h & 1) * 4, b * p.Lk + j * WS_BK, tc::smem_u32(&bar_vf[st]));
+        else
+          tc::bulk_g2s(tc::smem_u32(sV + st * V_TILE), Vp + static_cast<size_t>(j) * V_TILE, V_TILE, tc::smem_u32(&bar_vf[st]));
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // -------------------------------------------------------------------------- MMA issuer
-    const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, WS_BK), idesc_o = tc::idesc_ab(PARTS, AT_BM, AT_NV);
+    const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, WS_BK),
+                   idesc_o = tc::idesc_ab(PARTS, AT_BM, AT_NV) | (DIRECT ? tc::idesc_b_mn : 0u),
+                   idesc_1 = tc::idesc_ab(PARTS, AT_BM, 16);
     tc::mbar_wait(tc::smem_u32(&bar_q), 0);
     for (int j = 0; j <= nk; ++j) {  // iteration j: P.V of key tile j-1, then Q.K^T of key tile j
       for (int t = 0; t < nt; ++t) {
@@ -495,8 +517,12 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
 #pragma unroll
             for (int s = 0; s < WS_BK / 16; ++s) {  // 16 keys per step: 8 TMEM columns of packed bf16 pairs
               const uint32_t a_hi = tS + (s >> 1) * 32 + (s & 1) * 8;
-              const uint64_t dv = tc::smem_desc_sw128(va + (s >> 2) * V_BLK + (s & 3) * 32);
+              const uint64_t dv = DIRECT ? tc::smem_desc_sw128_mn(va + s * 2048)  // 16 keys = two 8-row swizzle atoms
+                                         : tc::smem_desc_sw128(va + (s >> 2) * V_BLK + (s & 3) * 32);
               tc::mma_bf16_ts(tO, a_hi, dv, idesc_o, s > 0 ? 1u : 0u);
+              if (DIRECT)  // row sums of P: column 48 of the accumulator
+                tc::mma_bf16_ts(tO + AT_NV, a_hi, tc::smem_desc_sw128(tc::smem_u32(sOnes) + (s >> 2) * ONES_BLK + (s & 3) * 32),
+                                idesc_1, s > 0 ? 1u : 0u);
               if (PARTS == 2) {
                 tc::mma_bf16_ts(tO, a_hi + 16, dv, idesc_o, 1u);
                 tc::mma_bf16_ts(tO, a_hi, tc::smem_desc_sw128(va + V_PART + (s >> 2) * V_BLK + (s & 3) * 32), idesc_o, 1u);
@@ -542,8 +568,10 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
         const int rr = e / 6, ch = e - rr * 6;  // rr = row within the CTA's nt * 128 queries
         const int q = qt0 * AT_BM + rr;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (q < p.Lq && ch * 8 < AT_HD) {
-          load_chunk8(p.Q, q_off + static_cast<long long>(q) * p.ldq + ch * 8, p.q16, ch * 8 + 4 < AT_HD, v);
+        const int d0 = ch * 8 - (DIRECT ? (h & 1) * 4 : 0);  // first head dim of the chunk (DIRECT, odd heads: shifted by 4)
+        const bool first = d0 >= 0 && d0 < AT_HD, second = d0 + 4 < AT_HD;
+        if (q < p.Lq && (first || second)) {
+          load_chunk8(p.Q, q_off + static_cast<long long>(q) * p.ldq + d0, p.q16, second, v, first);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] *= p.scale_log2;
         }
@@ -552,6 +580,12 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
         unsigned char *dst = sQ + (rr >> 7) * Q_TILE + tc::sw128_off(rr & 127, ch);
         *reinterpret_cast<uint4 *>(dst) = hi;
         if (PARTS == 2) *reinterpret_cast<uint4 *>(dst + QK_PART) = lo;
+      }
+      if (DIRECT) {  // constant tile of the row-sum MMA: row 0 (the first 128 bytes of each block) = 1.0 (fp16), rest 0
+        for (int e = tid - SM0 * 32; e < 2 * static_cast<int>(ONES_BLK) / 16; e += TILES * 128) {
+          const uint32_t one2 = (e & 127) < 8 ? 0x3C003C00u : 0u;
+          *reinterpret_cast<uint4 *>(sOnes + e * 16) = make_uint4(one2, one2, one2, one2);
+        }
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -564,7 +598,9 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
     const uint32_t tS = tmem + lane_base + t * 128, tO = tmem + lane_base + TM_O + t * 64;
     const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
     float m_run = -INFINITY, corr_prev = 1.f;
-    float o_acc[40];  // [0,36) output dims, [36] running softmax denominator, rest padding
+    float o_acc[40];  // [0,36) output dims, [36] running softmax denominator, rest padding (DIRECT: accumulator
+    // columns 0..39 — the head's dims at SHIFT .. SHIFT + 35 — and the denominator in l_dir)
+    float l_dir = 0.f;
 #pragma unroll
     for (int i = 0; i < 40; ++i) o_acc[i] = 0.f;
 
@@ -572,6 +608,12 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
       uint32_t a[32], c[8];
       tc::tmem_ld32(tO, a);
       tc::tmem_ld8(tO + 32, c);
+      if (DIRECT) {  // the row sum of P is column 48
+        uint32_t l;
+        tc::tmem_ld1(tO + AT_NV, l);
+        tc::tmem_ld_wait();
+        l_dir = fmaf(l_dir, corr_prev, __uint_as_float(l));
+      } else
       tc::tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], corr_prev, __uint_as_float(a[i]));
@@ -652,8 +694,12 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
     const int q = (qt0 + t) * AT_BM + row;
     if (q < p.Lq) {
       const long long o_off = b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
-      const float l_run = o_acc[AT_HD];
+      const float l_run = DIRECT ? l_dir : o_acc[AT_HD];
       const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
+      if (DIRECT && (h & 1)) {  // odd heads: the dims sit 4 columns up (static register indices in both branches)
+#pragma unroll
+        for (int d = 0; d < AT_HD; ++d) o_acc[d] = o_acc[d + 4];
+      }
 #pragma unroll
       for (int d = 0; d < AT_HD; d += 4) {
         float4 o4 = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
@@ -684,6 +730,11 @@ static int g_attn_impl = 1, g_attn_dbg = 0;
 // 80x1024 0.159 vs 0.187, 80x80 0.037 vs 0.046 — so the default is "always".  The bf16x3 mode keeps two ping-ponged
 // tiles per CTA: its operand tiles (hi + lo) leave room for one CTA per SM either way.
 static int g_attn_small_nk = 1 << 30;
+static int g_attn_direct = 1;  // fp16 K / V: tensor copies from the projection output instead of the pack kernel
+extern "C" int bd_attention_tc_set_direct(int on) {
+  g_attn_direct = on != 0;
+  return BD_OK;
+}
 extern "C" int bd_attention_tc_set_small_nk(int nk) {
   g_attn_small_nk = nk;
   return BD_OK;
@@ -761,7 +812,7 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
                                const float *V, int ldv, long long sv_b, const unsigned char *key_padding_mask,
                                float *O, int ldo, long long so_b, int B, int H, int Lq, int Lk, int hd, float scale,
                                int split, void *workspace, bd_stream_t stream, int phase, int io16) {
-  BD_REQUIRE(Q && K && V && O && workspace, "bd_attention_tc: null pointer");
+  BD_REQUIRE(Q && K && V && O, "bd_attention_tc: null pointer");
   BD_REQUIRE(io16 == 0 || (g_attn_impl == 1 && ldv % 4 == 0 && sv_b % 4 == 0 && (reinterpret_cast<uintptr_t>(V) & 7) == 0),
              "bd_attention_tc: fp16 tensors need the warp-specialised kernel and 8-byte aligned rows");
   BD_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && B <= 65535 && H <= 65535, "bd_attention_tc: bad sizes");
@@ -792,6 +843,8 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
   constexpr size_t WS_SMEM1 = 2 * (QK_PART + k_part(128) + v_part(128)) + 1024, WS_SMEM2 = 2 * WS_SMEM1 - 1024;
   // one query tile per CTA: Q tile + two stages of K and V^T
   constexpr size_t WS_SMEM1S = QK_PART + 2 * (k_part(128) + v_part(128)) + 1024, WS_SMEM2S = 2 * WS_SMEM1S - 1024;
+  // DIRECT: Q tile + two stages of (K tile, V tile of 128 keys x 128 B) + the ones tile
+  constexpr size_t WS_SMEM_DIRECT = QK_PART + 2 * (k_part(128) + 128 * 128) + 2 * ONES_BLK + 1024;
   static bd::PerDeviceOnce configured;  // function attributes are per device
   BD_CUDA(configured.run([&]() {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<1, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
@@ -800,6 +853,7 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1S);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2S);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_DIRECT);
     return e;
   }), "bd_attention_tc");
   cudaStream_t s = bd::as_stream(stream);
@@ -808,7 +862,27 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
     p.skip_q = 1;
     pgrid.x = 2 * p.nk;
     const bool small = (parts == 1 || g_attn_small_nk < (1 << 30)) && p.nk <= g_attn_small_nk;  // one query tile per CTA, two CTAs per SM
-    if (parts == 2) {
+    // fp16 K and V rows in HBM, dense batches: no pack kernel — the attention kernel's loader fetches the
+    // operand tiles from the projection output by tensor copies (phase 1 then has nothing to do)
+    const bool direct = g_attn_direct && parts == 1 && small && phase == 3 && p.k16 && p.v16 && ldk % 8 == 0 && ldv % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(K) & 15) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
+                        sk_b == static_cast<long long>(Lk) * ldk && sv_b == static_cast<long long>(Lk) * ldv;
+    BD_REQUIRE(direct || workspace, "bd_attention_tc: null workspace");
+    if (direct) {
+      tc::EncodeTiledFn enc = tc::encode_tiled();
+      BD_REQUIRE(enc != nullptr, "bd_attention_tc: cuTensorMapEncodeTiled is not available from this driver");
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(H) * AT_HD, static_cast<cuuint64_t>(B) * Lk};
+      const cuuint32_t box[2] = {64, WS_BK}, estr[2] = {1, 1};
+      for (int which = 0; which < 2; ++which) {
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(which ? ldv : ldk) * sizeof(__half)};
+        const CUresult r = enc(which ? &p.tmV : &p.tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                               const_cast<float *>(which ? V : K), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BD_REQUIRE(r == CUDA_SUCCESS, "bd_attention_tc: cuTensorMapEncodeTiled failed (%d) for B=%d Lk=%d ld=%d",
+                   static_cast<int>(r), B, Lk, which ? ldv : ldk);
+      }
+      BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");
+    } else if (parts == 2) {
       if (phase & 1) BD_CUDA(bd::launch_pdl(attention_pack_kernel<2, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
       if (!(phase & 2)) {
       } else if (small)
@@ -823,6 +897,8 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
       else
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 2>, wgrid, dim3(WS_THREADS), WS_SMEM1, s, p), "bd_attention_tc");
     }
+  } else if (!workspace) {
+    BD_REQUIRE(false, "bd_attention_tc: null workspace");
   } else if (parts == 2) {
     const size_t smem = 2 * (QK_PART + (k_part(64) + v_part(64)) + p_part(64)) + 1024;
     attention_pack_kernel<2, 64><<<pgrid, 256, 0, s>>>(p);

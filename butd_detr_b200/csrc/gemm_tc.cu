@@ -18,8 +18,6 @@
 //        or, for the fused variant (CTA owns complete rows, N <= 320), + residual -> LayerNorm.
 //
 // Replaces the cuBLAS / cuDNN-1x1-conv + BN + ReLU / LayerNorm call sites of the reference.
-#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
-
 #include "tc_common.cuh"
 
 namespace {
@@ -561,22 +559,8 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
   if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
+using tc::EncodeTiledFn;
+using tc::encode_tiled;
 
 int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   if (!p.g_idx && !(ln && p.A2)) {  // A (and A2) are read through the TMA unit

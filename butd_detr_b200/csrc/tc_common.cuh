@@ -14,11 +14,31 @@
 //     cp.async.bulk (TMA engine) signalled on an mbarrier.
 //   * accumulators live in TMEM: D[row i][col j] = lane i, column base + j (cta_group::1, M=128).
 #pragma once
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace tc {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
 
 constexpr int KB = 64;  // K elements per swizzle block (128 bytes of bf16)
 
@@ -108,6 +128,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
                : "memory");
@@ -132,6 +155,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   d |= 1ull << 46;
   d |= 2ull << 61;
   return d;
+}
+// shared-memory matrix descriptor, MN-MAJOR, SWIZZLE_128B: the operand lies in shared memory as rows of
+// 128 bytes = 64 consecutive elements along M / N for ONE k, 8 consecutive k per 1024-byte swizzle atom
+// (exactly what a 128-byte-swizzle tensor copy of a row-major [k][n] matrix produces); SBO = 1024 B between
+// groups of 8 k, LBO (between 64-element groups along M / N) unused for N <= 64.  A K = 16 step advances the
+// start address by 2048 B.  The instruction descriptor must carry the matching major bit (idesc_b_mn).
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) { return smem_desc_sw128(smem_addr); }
+constexpr uint32_t idesc_b_mn = 1u << 16;  // InstrDescriptor b_major = MN
+// 2-D tensor copy (TMA) global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
 }
 // instruction descriptor, kind::f16, A/B = bf16 K-major, D = f32 (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {

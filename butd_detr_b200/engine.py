@@ -95,6 +95,8 @@ HALF_ACT = True  # fp16 mode: activations that are only ever GEMM operands (FFN 
 # in HBM as fp16, and every LayerNorm output gets an fp16 copy that the next projections read by tensor copy straight
 # into the operand layout (bd_linear_tc_h / bd_linear_ln_tc_h) — the values are the ones the fp32 path rounds to fp16
 # inside the consumer anyway, the bytes are half
+DIRECT_KV = True  # fp16 mode: the attention kernel fetches K / V tiles from the projection output by tensor copies (no
+# pack kernel, no packed workspace); False = bd_attention_tc's pack kernel (A/B reference)
 TC_KC = 64  # k-chunk of the tensor-core kernels = one 128-byte swizzle block of bf16
 
 
@@ -404,10 +406,13 @@ class ForwardEngine:
             # out-projection's operand)
             out = self._empty(B * Lq, E, dtype=torch.float16)
             io = (int(q.dtype == torch.float16) | int(k.dtype == torch.float16) << 1 | int(v.dtype == torch.float16) << 2 | 8)
-            ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
+            direct = (DIRECT_KV and k.dtype == v.dtype == torch.float16 and k.stride(0) % 8 == 0 and v.stride(0) % 8 == 0
+                      and v.data_ptr() % 16 == 0)
+            ws = None if direct else self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split),
+                                                 dtype=torch.uint8)
             _lib.call("bd_attention_tc_h", q.data_ptr(), q.stride(0), Lq * q.stride(0), k.data_ptr(), k.stride(0),
                       Lk * k.stride(0), v.data_ptr(), v.stride(0), Lk * v.stride(0), _lib.ptr(mask), out.data_ptr(), E, Lq * E,
-                      io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), self.split, ws.data_ptr())
+                      io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), self.split, _lib.ptr(ws))
             return out
         assert q.dtype == k.dtype == v.dtype == torch.float32
         out = self._empty(B * Lq, E)
@@ -430,6 +435,8 @@ class ForwardEngine:
         k, v = kv[:, :E], kv[:, E:]
         if self.precision == "fp32" or hd != 36 or k.stride(0) % 4 or k.data_ptr() % 16 or v.data_ptr() % 16:
             return None
+        if self.half and DIRECT_KV and kv.dtype == torch.float16 and k.stride(0) % 8 == 0:
+            return None  # nothing to pack: the attention kernel reads these rows by tensor copies
         ws = self._empty(_lib.load().bd_attention_tc_workspace_bytes(B, H, Lq, Lk, self.split), dtype=torch.uint8)
         _lib.call("bd_attention_tc_pack_kv", k.data_ptr(), k.stride(0), Lk * k.stride(0), v.data_ptr(), v.stride(0),
                   Lk * v.stride(0), int(kv.dtype == torch.float16), B, H, Lq, Lk, hd, self.split, ws.data_ptr())

@@ -298,6 +298,12 @@ int bd_attention_tc_h(const void *Q, int ldq, long long sq_b, const void *K, int
  * Default: every length in the fp16 mode (measured faster at all of the model's shapes), none in the
  * bf16x3 mode; 0 = always the two-tile kernel; any other value applies to both modes. */
 int bd_attention_tc_set_small_nk(int nk);
+/* fp16 K AND V rows in HBM (io_half bits 1 and 2), split 1, dense batches (sk_b = Lk * ldk, sv_b = Lk * ldv), ldk / ldv
+ * multiples of 8 halfs, K / V 16-byte aligned: bd_attention_tc_h runs WITHOUT the pack kernel — the attention
+ * kernel's loader fetches each head's K and V tile from the projection output with one tensor copy each (128-byte
+ * swizzle; V stays [key][dim]: MN-major B operand; softmax denominators from an N = 16 MMA against a ones tile) —
+ * and `workspace` may be NULL.  on = 0 switches this off (A/B reference: the pack kernel).  Default on. */
+int bd_attention_tc_set_direct(int on);
 
 /* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n
  * logits, indices of the k largest sigmoid values, descending, ties -> lower index. n <= 4096 */

@@ -343,10 +343,15 @@ def test_linear_ln_tc_half_activations(cuda_lib, M, N, K, a_half, shadow):
         assert torch.equal(Y16, Y.half())
 
 
+@pytest.mark.parametrize("direct", [1, 0])
 @pytest.mark.parametrize("io", [15, 8, 9, 6, 14])
 @pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 1024, False), (3, 256, 132, True), (2, 80, 80, True), (1, 300, 1000, True)])
-def test_attention_tc_half_tensors(cuda_lib, B, Lq, Lk, masked, io):
-    """fp16 Q / K / V / O in HBM (io bits 0..3), fused wider buffers as in the engine."""
+def test_attention_tc_half_tensors(cuda_lib, B, Lq, Lk, masked, io, direct):
+    """fp16 Q / K / V / O in HBM (io bits 0..3), fused wider buffers as in the engine.  direct = 1: with fp16 K and V
+    (io bits 1, 2) the kernel reads its K / V tiles from these rows by tensor copies (no pack kernel, NULL
+    workspace); direct = 0: the pack kernel."""
+    if direct == 0 and (io & 6) != 6:
+        pytest.skip("same path as direct = 1")
     H, hd = 8, 36
     E = H * hd
     lib = cuda_lib.load()
@@ -363,10 +368,15 @@ def test_attention_tc_half_tensors(cuda_lib, B, Lq, Lk, masked, io):
         mask = (torch.arange(Lk)[None] >= lens[:, None]).cuda()
     out = torch.full((B, Lq, E), float("nan"), device="cuda", dtype=torch.float16 if io & 8 else torch.float32)
     m8 = mask.to(torch.uint8).contiguous() if masked else None
-    ws = torch.empty(lib.bd_attention_tc_workspace_bytes(B, H, Lq, Lk, 1), dtype=torch.uint8, device="cuda")
-    cuda_lib.call("bd_attention_tc_h", q.data_ptr(), E, Lq * E, k.data_ptr(), 2 * E, Lk * 2 * E, v.data_ptr(), 2 * E,
-                  Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), 1,
-                  ws.data_ptr())
+    no_ws = direct and (io & 6) == 6
+    ws = None if no_ws else torch.empty(lib.bd_attention_tc_workspace_bytes(B, H, Lq, Lk, 1), dtype=torch.uint8, device="cuda")
+    lib.bd_attention_tc_set_direct(direct)
+    try:
+        cuda_lib.call("bd_attention_tc_h", q.data_ptr(), E, Lq * E, k.data_ptr(), 2 * E, Lk * 2 * E, v.data_ptr(), 2 * E,
+                      Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, io, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), 1,
+                      cuda_lib.ptr(ws))
+    finally:
+        lib.bd_attention_tc_set_direct(1)
     qh = q32.reshape(B, Lq, H, hd).transpose(1, 2).double()
     kh = kv32[..., :E].reshape(B, Lk, H, hd).transpose(1, 2).double()
     vh = kv32[..., E:].reshape(B, Lk, H, hd).transpose(1, 2).double()
