@@ -18,11 +18,12 @@ attention_f32_kernel(const float *__restrict__ Q, int ldq, long long sq_b, const
                      long long sk_b, const float *__restrict__ V, int ldv, long long sv_b,
                      const unsigned char *__restrict__ mask, float *__restrict__ O, int ldo, long long so_b, int Lq,
                      int Lk, float scale) {
-  static_assert(HD % 4 == 0 && HD <= 36, "head_dim must be a multiple of 4 (static smem budget)");
-  __shared__ __align__(16) float Qt[HD][AT_LD];
-  __shared__ __align__(16) float Kt[HD][AT_LD];
-  __shared__ __align__(16) float Vs[AT_BK][HD];
-  __shared__ __align__(16) float Pt[AT_BK][AT_LD];
+  static_assert(HD % 4 == 0 && HD <= 64, "head_dim must be a multiple of 4, at most 64 (16 x HD / 4 <= 256 P.V threads)");
+  extern __shared__ __align__(16) float at_dyn[];  // attn_f32_smem(HD) bytes
+  float (*Qt)[AT_LD] = reinterpret_cast<float (*)[AT_LD]>(at_dyn);
+  float (*Kt)[AT_LD] = Qt + HD;
+  float (*Pt)[AT_LD] = Kt + HD;
+  float (*Vs)[HD] = reinterpret_cast<float (*)[HD]>(Pt + AT_BK);
   __shared__ float corr_s[AT_BQ], l_s[AT_BQ];
   __shared__ unsigned char kvalid[AT_BK];
 
@@ -145,6 +146,8 @@ attention_f32_kernel(const float *__restrict__ Q, int ldq, long long sq_b, const
   }
 }
 
+constexpr size_t attn_f32_smem(int hd) { return sizeof(float) * ((2 * hd + AT_BK) * AT_LD + AT_BK * hd); }
+
 }  // namespace
 
 extern "C" int bd_attention_f32(const float *Q, int ldq, long long sq_b, const float *K, int ldk, long long sk_b,
@@ -156,13 +159,21 @@ extern "C" int bd_attention_f32(const float *Q, int ldq, long long sq_b, const f
   dim3 grid(bd::ceil_div(Lq, AT_BQ), H, B);
   cudaStream_t s = bd::as_stream(stream);
   if (hd == 36)
-    attention_f32_kernel<36><<<grid, AT_THREADS, 0, s>>>(Q, ldq, sq_b, K, ldk, sk_b, V, ldv, sv_b, key_padding_mask, O,
-                                                         ldo, so_b, Lq, Lk, scale);
+    attention_f32_kernel<36><<<grid, AT_THREADS, attn_f32_smem(36), s>>>(Q, ldq, sq_b, K, ldk, sk_b, V, ldv, sv_b,
+                                                                         key_padding_mask, O, ldo, so_b, Lq, Lk, scale);
   else if (hd == 32)
-    attention_f32_kernel<32><<<grid, AT_THREADS, 0, s>>>(Q, ldq, sq_b, K, ldk, sk_b, V, ldv, sv_b, key_padding_mask, O,
-                                                         ldo, so_b, Lq, Lk, scale);
-  else {
-    bd::set_error("bd_attention_f32: head_dim %d not built (36 = d_model 288 / 8 heads, 32)", hd);
+    attention_f32_kernel<32><<<grid, AT_THREADS, attn_f32_smem(32), s>>>(Q, ldq, sq_b, K, ldk, sk_b, V, ldv, sv_b,
+                                                                         key_padding_mask, O, ldo, so_b, Lq, Lk, scale);
+  else if (hd == 64) {  // RoBERTa-base heads (the text encoder): 69 KB of shared memory
+    static bd::PerDeviceOnce configured;
+    BD_CUDA(configured.run([&]() {
+      return cudaFuncSetAttribute(attention_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(attn_f32_smem(64)));
+    }), "bd_attention_f32");
+    attention_f32_kernel<64><<<grid, AT_THREADS, attn_f32_smem(64), s>>>(Q, ldq, sq_b, K, ldk, sk_b, V, ldv, sv_b,
+                                                                         key_padding_mask, O, ldo, so_b, Lq, Lk, scale);
+  } else {
+    bd::set_error("bd_attention_f32: head_dim %d not built (36 = d_model 288 / 8 heads, 32, 64)", hd);
     return BD_ERR_UNSUPPORTED;
   }
   BD_CHECK_LAUNCH("bd_attention_f32");

@@ -429,9 +429,13 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long ne
 // SHIFT), so the foreign columns of K contribute exactly nothing, and the foreign columns of P.V are not read.  V stays in its natural [key][dim] layout: the B operand of P.V is MN-major.
 // The softmax denominator comes from a second, N = 16 MMA of P against a constant tile whose first row is ones.
 constexpr uint32_t ONES_BLK = 16 * 128;  // 16 rows x 64 keys
-template <int PARTS, int TILES, bool DIRECT = false>
-__global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES == 2 ? 1 : 2) attention_ws_kernel(const __grid_constant__ AttnParams p) {
+// HD = 64 (DIRECT only; RoBERTa-base heads of the text encoder): four K = 16 steps, P.V with N = 64, no shift.
+template <int PARTS, int TILES, bool DIRECT = false, int HD = AT_HD>
+__global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES == 2 || HD != AT_HD) ? 1 : 2) attention_ws_kernel(const __grid_constant__ AttnParams p) {
   static_assert(!DIRECT || (PARTS == 1 && TILES == 1), "DIRECT: fp16 operands, one query tile per CTA");
+  static_assert(HD == AT_HD || (HD == 64 && DIRECT), "head_dim 64 only with fp16 K / V rows (DIRECT)");
+  constexpr int NV = HD == AT_HD ? AT_NV : 64;  // accumulator columns of P.V (head dims padded to a multiple of 16)
+  constexpr int NO = HD == AT_HD ? 40 : 64;     // accumulator columns kept in registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t K_PART = k_part(WS_BK), V_PART = DIRECT ? WS_BK * 128u : v_part(WS_BK);
@@ -485,13 +489,13 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
         if (j >= 2) tc::mbar_wait(tc::smem_u32(&bar_ke[st]), par);
         tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_kf[st]), K_TILE);
         if (DIRECT)  // rows past this scene's keys (next scene / zero fill) are masked keys; the fill counts as bytes
-          tc::tma_load_2d(tc::smem_u32(sK + st * K_TILE), &p.tmK, h * AT_HD - (h & 1) * 4, b * p.Lk + j * WS_BK, tc::smem_u32(&bar_kf[st]));
+          tc::tma_load_2d(tc::smem_u32(sK + st * K_TILE), &p.tmK, HD == AT_HD ? h * AT_HD - (h & 1) * 4 : h * HD, b * p.Lk + j * WS_BK, tc::smem_u32(&bar_kf[st]));
         else
           tc::bulk_g2s(tc::smem_u32(sK + st * K_TILE), Kp + static_cast<size_t>(j) * K_TILE, K_TILE, tc::smem_u32(&bar_kf[st]));
         if (j >= 2) tc::mbar_wait(tc::smem_u32(&bar_ve[st]), par);
         tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_vf[st]), V_TILE);
         if (DIRECT)
-          tc::tma_load_2d(tc::smem_u32(sV + st * V_TILE), &p.tmV, h * AT_HD - (h & 1) * 4, b * p.Lk + j * WS_BK, tc::smem_u32(&bar_vf[st]));
+          tc::tma_load_2d(tc::smem_u32(sV + st * V_TILE), &p.tmV, HD == AT_HD ? h * AT_HD - (h & 1) * 4 : h * HD, b * p.Lk + j * WS_BK, tc::smem_u32(&bar_vf[st]));
         else
           tc::bulk_g2s(tc::smem_u32(sV + st * V_TILE), Vp + static_cast<size_t>(j) * V_TILE, V_TILE, tc::smem_u32(&bar_vf[st]));
       }
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
   } else if (warp == 1) {
     // -------------------------------------------------------------------------- MMA issuer
     const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, WS_BK),
-                   idesc_o = tc::idesc_ab(PARTS, AT_BM, AT_NV) | (DIRECT ? tc::idesc_b_mn : 0u),
+                   idesc_o = tc::idesc_ab(PARTS, AT_BM, NV) | (DIRECT ? tc::idesc_b_mn : 0u),
                    idesc_1 = tc::idesc_ab(PARTS, AT_BM, 16);
     tc::mbar_wait(tc::smem_u32(&bar_q), 0);
     for (int j = 0; j <= nk; ++j) {  // iteration j: P.V of key tile j-1, then Q.K^T of key tile j
@@ -521,7 +525,7 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
                                          : tc::smem_desc_sw128(va + (s >> 2) * V_BLK + (s & 3) * 32);
               tc::mma_bf16_ts(tO, a_hi, dv, idesc_o, s > 0 ? 1u : 0u);
               if (DIRECT)  // row sums of P: column 48 of the accumulator
-                tc::mma_bf16_ts(tO + AT_NV, a_hi, tc::smem_desc_sw128(tc::smem_u32(sOnes) + (s >> 2) * ONES_BLK + (s & 3) * 32),
+                tc::mma_bf16_ts(tO + NV, a_hi, tc::smem_desc_sw128(tc::smem_u32(sOnes) + (s >> 2) * ONES_BLK + (s & 3) * 32),
                                 idesc_1, s > 0 ? 1u : 0u);
               if (PARTS == 2) {
                 tc::mma_bf16_ts(tO, a_hi + 16, dv, idesc_o, 1u);
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
             const uint32_t q = tc::smem_u32(sQ + t * Q_TILE), k = tc::smem_u32(sK + st * K_TILE);
             if (!(p.dbg & 4))
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {  // head_dim 36 -> 48: three K=16 steps (the tile is padded to 64)
+            for (int s = 0; s < NV / 16; ++s) {  // head_dim 36 -> 48: three K=16 steps (the tile is padded to 64)
               const uint64_t dq = tc::smem_desc_sw128(q + s * 32), dk = tc::smem_desc_sw128(k + s * 32);
               tc::mma_bf16(tS, dq, dk, idesc_s, s > 0 ? 1u : 0u);
               if (PARTS == 2) {
@@ -563,13 +567,14 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
     // one reader, so it never goes through the pack kernel and HBM.  Item = (row, 16-byte chunk
     // of 8 head dims); chunks 0..5 cover the three K = 16 steps (36 dims, rest zero).
     {
-      const long long q_off = b * p.sq_b + h * AT_HD;
-      for (int e = tid - SM0 * 32; e < nt * AT_BM * 6; e += TILES * 128) {
-        const int rr = e / 6, ch = e - rr * 6;  // rr = row within the CTA's nt * 128 queries
+      const long long q_off = b * p.sq_b + h * HD;
+      constexpr int NCH = NV / 8;  // 16-byte chunks the MMAs read per row
+      for (int e = tid - SM0 * 32; e < nt * AT_BM * NCH; e += TILES * 128) {
+        const int rr = e / NCH, ch = e - rr * NCH;  // rr = row within the CTA's nt * 128 queries
         const int q = qt0 * AT_BM + rr;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int d0 = ch * 8 - (DIRECT ? (h & 1) * 4 : 0);  // first head dim of the chunk (DIRECT, odd heads: shifted by 4)
-        const bool first = d0 >= 0 && d0 < AT_HD, second = d0 + 4 < AT_HD;
+        const int d0 = ch * 8 - ((DIRECT && HD == AT_HD) ? (h & 1) * 4 : 0);  // first head dim of the chunk (DIRECT, odd heads: shifted by 4)
+        const bool first = d0 >= 0 && d0 < HD, second = d0 + 4 < HD;
         if (q < p.Lq && (first || second)) {
           load_chunk8(p.Q, q_off + static_cast<long long>(q) * p.ldq + d0, p.q16, second, v, first);
 #pragma unroll
@@ -598,19 +603,20 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
     const uint32_t tS = tmem + lane_base + t * 128, tO = tmem + lane_base + TM_O + t * 64;
     const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
     float m_run = -INFINITY, corr_prev = 1.f;
-    float o_acc[40];  // [0,36) output dims, [36] running softmax denominator, rest padding (DIRECT: accumulator
+    float o_acc[NO];  // [0,36) output dims, [36] running softmax denominator, rest padding (DIRECT: accumulator
     // columns 0..39 — the head's dims at SHIFT .. SHIFT + 35 — and the denominator in l_dir)
     float l_dir = 0.f;
 #pragma unroll
-    for (int i = 0; i < 40; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < NO; ++i) o_acc[i] = 0.f;
 
     auto fold_o = [&]() {  // o_acc = o_acc * corr + Ot (result of the previous key tile)
-      uint32_t a[32], c[8];
+      uint32_t a[32], c[NO - 32];
       tc::tmem_ld32(tO, a);
-      tc::tmem_ld8(tO + 32, c);
-      if (DIRECT) {  // the row sum of P is column 48
+      if constexpr (NO == 40) tc::tmem_ld8(tO + 32, c);
+      else tc::tmem_ld32(tO + 32, c);
+      if (DIRECT) {  // the row sum of P is the first column after the head dims
         uint32_t l;
-        tc::tmem_ld1(tO + AT_NV, l);
+        tc::tmem_ld1(tO + NV, l);
         tc::tmem_ld_wait();
         l_dir = fmaf(l_dir, corr_prev, __uint_as_float(l));
       } else
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], corr_prev, __uint_as_float(a[i]));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], corr_prev, __uint_as_float(c[i]));
+      for (int i = 0; i < NO - 32; ++i) o_acc[32 + i] = fmaf(o_acc[32 + i], corr_prev, __uint_as_float(c[i]));
     };
 
     for (int j = 0; j < nk; ++j) {
@@ -693,15 +699,15 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, TILES =
 
     const int q = (qt0 + t) * AT_BM + row;
     if (q < p.Lq) {
-      const long long o_off = b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
+      const long long o_off = b * p.so_b + static_cast<long long>(q) * p.ldo + h * HD;
       const float l_run = DIRECT ? l_dir : o_acc[AT_HD];
       const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
-      if (DIRECT && (h & 1)) {  // odd heads: the dims sit 4 columns up (static register indices in both branches)
+      if (DIRECT && HD == AT_HD && (h & 1)) {  // odd heads: the dims sit 4 columns up (static register indices in both branches)
 #pragma unroll
         for (int d = 0; d < AT_HD; ++d) o_acc[d] = o_acc[d + 4];
       }
 #pragma unroll
-      for (int d = 0; d < AT_HD; d += 4) {
+      for (int d = 0; d < HD; d += 4) {
         float4 o4 = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
         if (l_run == 0.f) o4 = make_float4(NAN, NAN, NAN, NAN);
         if (p.o16) {  // fp16 rows: the out-projection reads them as its operand (8-byte aligned: ld % 4 == 0)
@@ -816,13 +822,14 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
   BD_REQUIRE(io16 == 0 || (g_attn_impl == 1 && ldv % 4 == 0 && sv_b % 4 == 0 && (reinterpret_cast<uintptr_t>(V) & 7) == 0),
              "bd_attention_tc: fp16 tensors need the warp-specialised kernel and 8-byte aligned rows");
   BD_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && B <= 65535 && H <= 65535, "bd_attention_tc: bad sizes");
-  BD_REQUIRE(hd == AT_HD, "bd_attention_tc: built for head_dim 36 (d_model 288 / 8 heads)");
+  BD_REQUIRE(hd == AT_HD || hd == 64, "bd_attention_tc: built for head_dim 36 (d_model 288 / 8 heads) and 64 (fp16 K / V only)");
   BD_REQUIRE(split == 1 || split == 3, "bd_attention_tc: split must be 1 (bf16) or 3 (bf16x3)");
   BD_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && sq_b % 4 == 0 && sk_b % 4 == 0 &&
                  (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
              "bd_attention_tc: Q / K rows and the workspace must be 16-byte aligned");
   const int impl = g_attn_impl;
+  BD_REQUIRE(hd == AT_HD || impl == 1, "bd_attention_tc: head_dim 64 only with the warp-specialised kernel");
   BD_REQUIRE(impl == 0 || (ldo % 4 == 0 && so_b % 4 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0),
              "bd_attention_tc: output rows must be 16-byte aligned");
   const int BK = attn_bk(split);
@@ -854,6 +861,7 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM1S);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2S);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_DIRECT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_DIRECT);
     return e;
   }), "bd_attention_tc");
   cudaStream_t s = bd::as_stream(stream);
@@ -864,14 +872,16 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
     const bool small = (parts == 1 || g_attn_small_nk < (1 << 30)) && p.nk <= g_attn_small_nk;  // one query tile per CTA, two CTAs per SM
     // fp16 K and V rows in HBM, dense batches: no pack kernel — the attention kernel's loader fetches the
     // operand tiles from the projection output by tensor copies (phase 1 then has nothing to do)
-    const bool direct = g_attn_direct && parts == 1 && small && phase == 3 && p.k16 && p.v16 && ldk % 8 == 0 && ldv % 8 == 0 &&
+    const bool direct = (g_attn_direct || hd == 64) && parts == 1 && small && phase == 3 && p.k16 && p.v16 && ldk % 8 == 0 && ldv % 8 == 0 &&
                         (reinterpret_cast<uintptr_t>(K) & 15) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
                         sk_b == static_cast<long long>(Lk) * ldk && sv_b == static_cast<long long>(Lk) * ldv;
     BD_REQUIRE(direct || workspace, "bd_attention_tc: null workspace");
+    BD_REQUIRE(direct || hd == AT_HD, "bd_attention_tc: head_dim 64 needs fp16 K and V rows (io_half bits 1, 2), split 1, dense "
+                                      "batches, ldk / ldv multiples of 8 and 16-byte aligned K / V");
     if (direct) {
       tc::EncodeTiledFn enc = tc::encode_tiled();
       BD_REQUIRE(enc != nullptr, "bd_attention_tc: cuTensorMapEncodeTiled is not available from this driver");
-      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(H) * AT_HD, static_cast<cuuint64_t>(B) * Lk};
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(H) * hd, static_cast<cuuint64_t>(B) * Lk};
       const cuuint32_t box[2] = {64, WS_BK}, estr[2] = {1, 1};
       for (int which = 0; which < 2; ++which) {
         const cuuint64_t strides[1] = {static_cast<cuuint64_t>(which ? ldv : ldk) * sizeof(__half)};
@@ -881,7 +891,10 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
         BD_REQUIRE(r == CUDA_SUCCESS, "bd_attention_tc: cuTensorMapEncodeTiled failed (%d) for B=%d Lk=%d ld=%d",
                    static_cast<int>(r), B, Lk, which ? ldv : ldk);
       }
-      BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");
+      if (hd == 64)
+        BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true, 64>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");
+      else
+        BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");
     } else if (parts == 2) {
       if (phase & 1) BD_CUDA(bd::launch_pdl(attention_pack_kernel<2, 128>, pgrid, dim3(256), 0, s, p), "bd_attention_tc");
       if (!(phase & 2)) {

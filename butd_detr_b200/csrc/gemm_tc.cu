@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float v = __uint_as_float(acc[u][j]) + bias_s[(g + u) * 16 + j];
-            if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
+            if (!LN_EPI && p.relu == 1) v = fmaxf(v, 0.f);
+            if (!LN_EPI && p.relu == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // exact (erf) GELU: RoBERTa's FFN
             o[j] = v;
           }
           if (EPI == 0 && p.y16) {  // fp16 rows: row stride NC + 8 halfs

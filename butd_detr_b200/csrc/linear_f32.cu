@@ -137,7 +137,8 @@ linear_f32_kernel(const float *__restrict__ A, int lda, const float *__restrict_
       const int gc = col0 + tx * TN + j;
       if (gc >= N) continue;
       float v = acc[i][j] + (bias ? __ldg(bias + gc) : 0.f);
-      if (relu) v = fmaxf(v, 0.f);
+      if (relu == 1) v = fmaxf(v, 0.f);
+      if (relu == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // exact (erf) GELU
       Y[static_cast<long long>(gr) * ldy + gc] = v;
     }
   }

@@ -78,6 +78,63 @@ add_layernorm_kernel(const float *__restrict__ X, const float *__restrict__ R, c
   }
 }
 
+// RoBERTa input embeddings (the text side; transformers' RobertaEmbeddings.forward as
+// called from /root/reference/models/bdetr.py:168): word[id] + position[pid] + token_type[0] -> LayerNorm, with
+// pid = pad_idx + (number of non-pad tokens up to and including this one) for a non-pad token, pad_idx for a pad
+// token.  One warp per token; ids outside the tables are clamped (no fault on a bad id).
+__global__ void __launch_bounds__(256)
+roberta_embed_kernel(const long long *__restrict__ ids, const float *__restrict__ word, int vocab,
+                     const float *__restrict__ pos, int n_pos, const float *__restrict__ type,
+                     const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ Y, int B, int L,
+                     int D, int pad_idx, float eps) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<long long>(B) * L) return;
+  const int l = static_cast<int>(row % L);
+  const long long *rid = ids + (row - l);
+  int cnt = 0;
+  for (int i = lane; i <= l; i += 32) cnt += rid[i] != pad_idx;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, off);
+  long long id = rid[l];
+  int pid = id != pad_idx ? pad_idx + cnt : pad_idx;
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  pid = pid >= n_pos ? n_pos - 1 : pid;
+  const float *w = word + id * D, *pe = pos + static_cast<long long>(pid) * D;
+  float v[LN_MAX_PER_LANE];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    v[i] = 0.f;
+    if (c < D) {
+      v[i] = __ldg(w + c) + __ldg(pe + c) + __ldg(type + c);
+      sum += v[i];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+  const float mean = sum / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < D) {
+      const float d = v[i] - mean;
+      sq = fmaf(d, d, sq);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
+  const float rstd = rsqrtf(sq / static_cast<float>(D) + eps);
+  float *y = Y + row * D;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < D) y[c] = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+  }
+}
+
 // Query selection: sigmoid, then a full bitonic sort of (value, ~index) keys in shared memory.
 constexpr int TOPK_MAX = 4096;
 __global__ void __launch_bounds__(1024)
@@ -178,6 +235,19 @@ int bd_add_layernorm_f32(const float *X, const float *R, const float *gamma, con
   BD_REQUIRE(M > 0 && D > 0 && D <= 32 * LN_MAX_PER_LANE, "bd_add_layernorm_f32: bad sizes (D <= 1024)");
   add_layernorm_kernel<<<bd::ceil_div(M, 8), 256, 0, bd::as_stream(stream)>>>(X, R, gamma, beta, Y, M, D, eps);
   BD_CHECK_LAUNCH("bd_add_layernorm_f32");
+  return BD_OK;
+}
+
+int bd_roberta_embed(const long long *ids, const float *word, int vocab, const float *pos, int n_pos, const float *type,
+                     const float *gamma, const float *beta, float *Y, int B, int L, int D, int pad_idx, float eps,
+                     bd_stream_t stream) {
+  BD_REQUIRE(ids && word && pos && type && gamma && beta && Y, "bd_roberta_embed: null pointer");
+  BD_REQUIRE(B > 0 && L > 0 && D > 0 && D <= 32 * LN_MAX_PER_LANE && vocab > 0 && n_pos > pad_idx && pad_idx >= 0,
+             "bd_roberta_embed: bad sizes (D <= 1024, pad_idx < n_pos)");
+  const long long rows = static_cast<long long>(B) * L;
+  roberta_embed_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, bd::as_stream(stream)>>>(
+      ids, word, vocab, pos, n_pos, type, gamma, beta, Y, B, L, D, pad_idx, eps);
+  BD_CHECK_LAUNCH("bd_roberta_embed");
   return BD_OK;
 }
 

@@ -10,9 +10,13 @@ Keeps what `train_dist_mod.py` / `main_utils.py` / `models/losses.py` /
   * `forward(inputs) -> end_points` with the key schema of SURVEY.md Appendix B.
 
 The forward itself does not run PyTorch layers: it hands the tensors to
-`engine.ForwardEngine`, i.e. to the sm_100a kernels behind the C-ABI.  Only the frozen RoBERTa
-text encoder (third-party, out of scope — SURVEY.md §2.1 #14) stays a transformers module; feed
-`inputs['text_hidden']` + `inputs['text_attention_mask']` to bypass it.
+`engine.ForwardEngine`, i.e. to the sm_100a kernels behind the C-ABI.  The frozen RoBERTa text
+encoder keeps its transformers module as the parameter container (state_dict keys `text_encoder.*`
+as in the reference), but its forward runs on the same kernels (`text_encoder.RobertaEngine`,
+SURVEY.md §8f rank 2; `native_text_encoder=False` calls the transformers module instead).  Only the
+tokenizer (host string processing) stays transformers'.  Feed `inputs['text_hidden']` +
+`inputs['text_attention_mask']` to bypass the text side, or `inputs['input_ids']` +
+`inputs['text_attention_mask']` to bypass just the tokenizer.
 
 `model.eval()` (the graded path) runs the engine: BatchNorm on running statistics, dropout off,
 no autograd.  `model.train()` runs the training forward of butd_detr_b200/train.py: an autograd
@@ -62,7 +66,8 @@ class BeaUTyDETR(nn.Module):
     def __init__(self, num_class=256, num_obj_class=485, input_feature_dim=3, num_queries=256,
                  num_decoder_layers=6, self_position_embedding='loc_learned', contrastive_align_loss=True,
                  d_model=288, butd=True, pointnet_ckpt=None, self_attend=True, *,
-                 text_encoder="roberta-base", num_encoder_layers=3, cuda_graph=False, precision="fp32"):
+                 text_encoder="roberta-base", num_encoder_layers=3, cuda_graph=False, precision="fp32",
+                 native_text_encoder=True):
         super().__init__()
         if self_position_embedding not in ("none", "xyz_learned", "loc_learned"):
             raise NotImplementedError(self_position_embedding)
@@ -86,6 +91,9 @@ class BeaUTyDETR(nn.Module):
         # static outputs: they are overwritten by the next forward with the same input shapes — clone
         # what must outlive the next call.
         self.cuda_graph = cuda_graph
+        self.native_text_encoder = native_text_encoder  # RoBERTa forward on the sm_100a kernels (text_encoder.py)
+        self._text_engine = None
+        self._text_engine_key = None
         self.train_dropout = True  # False: every dropout of the training forward off (deterministic; parity tests)
         self._engine = None
         self._engine_key = None
@@ -246,6 +254,7 @@ class BeaUTyDETR(nn.Module):
         """Drop the packed (BN-folded) weights; they are rebuilt on the next forward."""
         self._engine = None
         self._weight_tensors = None
+        self._text_engine = None
 
     def _on_load_state_dict(self, module, incompatible_keys):
         self.invalidate_engine()
@@ -269,6 +278,17 @@ class BeaUTyDETR(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def text_engine(self, device):
+        """RoBERTa forward engine over `self.text_encoder`'s weights, in this model's precision (rebuilt when the
+        weights change or move)."""
+        ps = list(self.text_encoder.parameters())
+        key = (torch.device(device), self.cfg["precision"], sum(p._version for p in ps), ps[0].data_ptr())
+        if self._text_engine is None or self._text_engine_key != key:
+            from . import text_encoder as te
+            self._text_engine = te.from_module(self.text_encoder, self.cfg["precision"], device)
+            self._text_engine_key = key
+        return self._text_engine
+
     # ------------------------------------------------------------------ forward
     def _encode_text(self, inputs, device):
         """tokenizer -> RoBERTa (bdetr.py:164-171); returns (hidden (B,L,768), HF mask, tokenized).
@@ -281,13 +301,24 @@ class BeaUTyDETR(nn.Module):
             if "input_ids" in inputs:
                 tok["input_ids"] = inputs["input_ids"].to(device)
             return inputs["text_hidden"].to(device), mask, BatchEncoding(tok)
-        if self.text_encoder is None or self.tokenizer is None:
-            raise RuntimeError("no tokenizer/text encoder available: provide inputs['text_hidden'] "
-                               "(B,L,768) and inputs['text_attention_mask'] (B,L)")
-        tokenized = self.tokenizer.batch_encode_plus(inputs["text"], padding="longest", return_tensors="pt").to(device)
-        with torch.no_grad():
-            hidden = self.text_encoder(**tokenized).last_hidden_state
-        return hidden, tokenized.attention_mask, tokenized
+        if "input_ids" in inputs:  # already tokenized (the tokenizer is host string processing, not part of this package)
+            from transformers import BatchEncoding
+            tokenized = BatchEncoding({"input_ids": inputs["input_ids"].to(device),
+                                       "attention_mask": inputs["text_attention_mask"].to(device)})
+        else:
+            if self.tokenizer is None:
+                raise RuntimeError("no tokenizer available: provide inputs['input_ids'] + inputs['text_attention_mask'], "
+                                   "or inputs['text_hidden'] (B,L,768) + inputs['text_attention_mask'] (B,L)")
+            tokenized = self.tokenizer.batch_encode_plus(inputs["text"], padding="longest", return_tensors="pt").to(device)
+        if self.text_encoder is None:
+            raise RuntimeError("no text encoder available: provide inputs['text_hidden'] (B,L,768) and "
+                               "inputs['text_attention_mask'] (B,L)")
+        if self.native_text_encoder:
+            hidden = self.text_engine(device).forward(tokenized["input_ids"], tokenized["attention_mask"])
+        else:
+            with torch.no_grad():
+                hidden = self.text_encoder(**tokenized).last_hidden_state
+        return hidden, tokenized["attention_mask"], tokenized
 
     def forward(self, inputs, overrides=None):
         """inputs: {point_clouds (B,N,3+C), text: list[str] | (text_hidden, text_attention_mask),

@@ -159,7 +159,8 @@ int bd_fp_interp_concat(const float *dist2, const int *idx, const float *known_f
 
 /* Y = act( (A [+ A2]) · Wᵀ + bias ) : A (M,K) lda, A2 optional same shape (lda2), W (N,K)
  * row-major (torch Linear / 1x1-conv weight, BatchNorm folded by the host), bias (N) or NULL,
- * Y (M,N) ldy.  relu != 0 applies max(.,0).  fp32 SIMT path (1e-3 parity gate). */
+ * Y (M,N) ldy.  relu = 1 applies max(.,0), relu = 2 the exact (erf) GELU of RoBERTa's feed-forward block (the
+ * same codes hold for bd_linear_tc / bd_linear_tc_h).  fp32 SIMT path (1e-3 parity gate). */
 int bd_linear_f32(const float *A, int lda, const float *A2, int lda2, const float *W,
                   const float *bias, float *Y, int ldy, int M, int N, int K, int relu,
                   bd_stream_t stream);
@@ -304,6 +305,14 @@ int bd_attention_tc_set_small_nk(int nk);
  * swizzle; V stays [key][dim]: MN-major B operand; softmax denominators from an N = 16 MMA against a ones tile) —
  * and `workspace` may be NULL.  on = 0 switches this off (A/B reference: the pack kernel).  Default on. */
 int bd_attention_tc_set_direct(int on);
+
+/* RoBERTa input embeddings (text side, reference call site models/bdetr.py:168 -> transformers
+ * RobertaEmbeddings.forward): Y (B*L, D) = LayerNorm(word[ids] + position[pid] + token_type[0]) with
+ * pid = pad_idx + running count of non-pad tokens (pad tokens: pad_idx).  ids (B,L) int64; word (vocab,D),
+ * position (n_pos,D), type (>=1,D) fp32; D <= 1024.  Out-of-table ids are clamped. */
+int bd_roberta_embed(const long long *ids, const float *word, int vocab, const float *pos, int n_pos,
+                     const float *type, const float *gamma, const float *beta, float *Y, int B, int L,
+                     int D, int pad_idx, float eps, bd_stream_t stream);
 
 /* torch.topk(sigmoid(logits), k)[1].int() (models/bdetr.py:181-184): per batch row of n
  * logits, indices of the k largest sigmoid values, descending, ties -> lower index. n <= 4096 */
