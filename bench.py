@@ -211,6 +211,7 @@ def main():
                          "BASELINE.json configs[1] names, outputs within its 1e-2 gate (default); bf16x3 = tcgen05 "
                          "with bf16 hi/lo split operands, outputs within the fp32 gate 1e-3; fp32 = SIMT kernels")
     ap.add_argument("--cpu-scenes", type=int, default=3, help="scenes timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--no-text-side", action="store_true", help="skip the RoBERTa-forward measurement (text side)")
     ap.add_argument("--no-train-step", action="store_true",
                     help="skip the configs[2] measurement (training step at global batch 8 with the gradient all-reduce)")
     args = ap.parse_args()
@@ -427,6 +428,11 @@ def main():
                "unit": "scenes/s", "steps": 5, "output_gate": PARITY_GATE[other]}
         del m2
 
+    # ---------------- text side: RoBERTa-base forward on the same kernels
+    text_side = None
+    if rank == 0 and not args.no_text_side:
+        text_side = measure_text_side(dev, B, args.precision, scenes / (ms_total * 1e-3) / world)
+
     # ---------------- configs[2]: one training step at GLOBAL batch 8, data-parallel, ONE gradient all-reduce
     train_step = None
     if not args.no_train_step:
@@ -455,7 +461,7 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "latency_b1": latency, "other_precision": alt,
-                "parity": parity, "train_step": train_step,
+                "parity": parity, "train_step": train_step, "text_side": text_side,
                 "attention": attention_summary(scenes / (ms_total * 1e-3) / world, rooflines if kernel_table else []),
                 "rooflines_top": rooflines[:6] if kernel_table else None,
                 "kernels": kernel_table[:40] if kernel_table else None}
@@ -463,6 +469,44 @@ def main():
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_text_side(dev, B, precision, visual_scenes_per_s, L=None, steps=5, warmup=3):
+    """The step immediately upstream of configs[1]: tokens -> RoBERTa-base (12 layers,
+    768 wide, 12 heads of 64) -> last_hidden_state, on this library's kernels (butd_detr_b200/text_encoder.py), for
+    one batch of B utterances of L tokens.  Random-initialised weights of the architecture (no hub access), random
+    token ids; device-resident inputs, CUDA events."""
+    import torch
+    from transformers import RobertaConfig, RobertaModel
+    from butd_detr_b200 import _lib, text_encoder
+    L = L or WORKLOAD["n_tokens"]
+    cfg = RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1)
+    torch.manual_seed(0)
+    eng = text_encoder.from_module(RobertaModel(cfg), precision, dev)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(3, cfg.vocab_size, (B, L), generator=g).to(dev)
+    mask = torch.ones(B, L, dtype=torch.long, device=dev)
+    for _ in range(warmup):
+        eng.forward(ids, mask)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        out = eng.forward(ids, mask)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    E, H, F, nl = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size, cfg.num_hidden_layers
+    flops_scene = nl * (2 * L * (3 * E * E + E * E + 2 * E * F) + 4 * L * L * E)
+    text_sps = B / (ms * 1e-3)
+    return {"workload": f"RoBERTa-base forward, {B} utterances x {L} tokens, {precision}", "ms_per_batch": ms,
+            "scenes_per_s": text_sps, "gflop_per_scene": flops_scene / 1e9,
+            "tflops": flops_scene * text_sps / 1e12, "flop_roofline_frac": flops_scene * text_sps / 1e12 / tensor_peak(),
+            "launches_per_forward": (_lib.launch_count - n0) // steps, "output_finite": bool(torch.isfinite(out).all()),
+            "scenes_per_s_text_plus_visual": 1.0 / (1.0 / text_sps + 1.0 / visual_scenes_per_s),
+            "weights": "random-initialised RoBERTa-base architecture (no hub access); parity vs the transformers module: "
+                       "tests/test_gpu_text_encoder.py"}
 
 
 def measure_train_step(dev, rank, world, pool_dev, global_batch=8, steps=4, warmup=2):

@@ -66,7 +66,9 @@ struct LinearTcParams {
 
 // MODE: 0 = A, 1 = A + A2, 2 = gathered rows (QueryAndGroup).  EPI: 0 = bias/ReLU, 1 = residual + LayerNorm,
 // 2 = bias/ReLU + max-pool over groups of rows.
-template <int EPI, int MODE>
+// GELU: the plain epilogue applies the exact (erf) GELU instead of ReLU — its own instantiation, because erff() inside
+// the shared epilogue loop costs every other linear of the forward (measured: 7.8 % of the whole step).
+template <int EPI, int MODE, bool GELU = false>
 __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) linear_tc_kernel(const __grid_constant__ LinearTcParams p) {
   constexpr bool LN_EPI = EPI == 1;
   constexpr bool HAS_A2 = MODE == 1;
@@ -416,8 +418,8 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float v = __uint_as_float(acc[u][j]) + bias_s[(g + u) * 16 + j];
-            if (!LN_EPI && p.relu == 1) v = fmaxf(v, 0.f);
-            if (!LN_EPI && p.relu == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // exact (erf) GELU: RoBERTa's FFN
+            if (GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // exact (erf) GELU: RoBERTa's FFN
+            else if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
             o[j] = v;
           }
           if (EPI == 0 && p.y16) {  // fp16 rows: row stride NC + 8 halfs
@@ -617,7 +619,8 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
     cudaError_t e = cudaSuccess;
     const void *kernels[] = {(const void *)linear_tc_kernel<0, 0>, (const void *)linear_tc_kernel<0, 1>,
                              (const void *)linear_tc_kernel<1, 0>, (const void *)linear_tc_kernel<1, 1>,
-                             (const void *)linear_tc_kernel<0, 2>, (const void *)linear_tc_kernel<2, 0>};
+                             (const void *)linear_tc_kernel<0, 2>, (const void *)linear_tc_kernel<2, 0>,
+                             (const void *)linear_tc_kernel<0, 0, true>};
     for (const void *k : kernels)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
     return e;
@@ -625,6 +628,8 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
   const int n_groups = bd::ceil_div(p.N, NC);
   BD_REQUIRE(n_groups <= 65535, "bd_linear_tc: N too large");
   dim3 grid(bd::ceil_div(p.M, TC_BM), n_groups);
+  BD_REQUIRE(p.relu != 2 || (!p.g_idx && p.pool <= 0 && !ln && !p.A2),
+             "bd_linear_tc: the GELU epilogue (relu = 2) exists for the plain A, plain epilogue variant only");
   if (p.g_idx)
     BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 2>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else if (p.pool > 0)
@@ -635,6 +640,8 @@ int launch_linear_tc(LinearTcParams &p, bool ln, cudaStream_t stream) {
     BD_CUDA(bd::launch_pdl(linear_tc_kernel<1, 0>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else if (p.A2)
     BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 1>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
+  else if (p.relu == 2)
+    BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 0, true>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   else
     BD_CUDA(bd::launch_pdl(linear_tc_kernel<0, 0>, grid, dim3(TC_THREADS), smem, stream, p), "bd_linear_tc");
   return BD_OK;
