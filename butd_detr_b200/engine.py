@@ -125,7 +125,9 @@ def lin_tiling(M, N, n_sm=148):
     nt = -(-N // 160)
     bn = _round_up(-(-N // nt), 16)
     if rows * nt > n_sm:
-        return (N > 160), None           # more than a wave anyway: wide tiles, fewer A stagings
+        # more than a wave anyway: wide tiles, fewer A stagings (re-measured with fp16 A rows at 148 scenes: one
+        # accumulator per CTA and two CTAs per SM is 3.5 % slower over the whole forward)
+        return (N > 160), None
     # (accumulators narrower than the default were measured too: no gain — a CTA's time is its
     #  operand-load chain, not its MMA / write-out width)
     return False, None
