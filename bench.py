@@ -433,6 +433,8 @@ def main():
     if rank == 0 and not args.no_text_side:
         text_side = measure_text_side(dev, B, args.precision, scenes / (ms_total * 1e-3) / world)
 
+    matcher = measure_matcher(dev) if rank == 0 and not args.no_text_side else None
+
     # ---------------- configs[2]: one training step at GLOBAL batch 8, data-parallel, ONE gradient all-reduce
     train_step = None
     if not args.no_train_step:
@@ -461,7 +463,7 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "latency_b1": latency, "other_precision": alt,
-                "parity": parity, "train_step": train_step, "text_side": text_side,
+                "parity": parity, "train_step": train_step, "text_side": text_side, "matcher": matcher,
                 "attention": attention_summary(scenes / (ms_total * 1e-3) / world, rooflines if kernel_table else []),
                 "rooflines_top": rooflines[:6] if kernel_table else None,
                 "kernels": kernel_table[:40] if kernel_table else None}
@@ -507,6 +509,37 @@ def measure_text_side(dev, B, precision, visual_scenes_per_s, L=None, steps=5, w
             "scenes_per_s_text_plus_visual": 1.0 / (1.0 / text_sps + 1.0 / visual_scenes_per_s),
             "weights": "random-initialised RoBERTa-base architecture (no hub access); parity vs the transformers module: "
                        "tests/test_gpu_text_encoder.py"}
+
+
+def measure_matcher(dev, B=8, Q=256, C=256, steps=20):
+    """Device-side Hungarian matcher (butd_detr_b200/matcher.py): one call = cost matrix +
+    assignment for a batch of 8 scenes (the reference calls its host-side matcher once per prediction head, 7 times
+    per training step, each with a device-to-host copy and scipy)."""
+    import torch
+    from butd_detr_b200.matcher import HungarianMatcher
+    g = torch.Generator().manual_seed(2)
+    sizes = [int(x) for x in torch.randint(4, 65, (B,), generator=g)]
+    out = {"pred_logits": torch.randn(B, Q, C, generator=g).to(dev),
+           "pred_boxes": torch.cat([torch.rand(B, Q, 3, generator=g) * 4 - 2, torch.rand(B, Q, 3, generator=g) + 0.05], -1).to(dev)}
+    targets = []
+    for n in sizes:
+        pm = torch.zeros(n, 256)
+        pm[torch.arange(n), torch.randint(0, C, (n,), generator=g)] = 1.0
+        targets.append({"boxes": torch.cat([torch.rand(n, 3, generator=g) * 4 - 2, torch.rand(n, 3, generator=g) + 0.05], -1).to(dev),
+                        "positive_map": pm.to(dev), "labels": torch.zeros(n, dtype=torch.int64, device=dev)})
+    m = HungarianMatcher(1, 0, 2, True)
+    for _ in range(3):
+        m(out, targets)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        m(out, targets)
+    t1.record()
+    torch.cuda.synchronize()
+    return {"workload": f"cost matrix + optimal assignment, {B} scenes x {Q} queries, {sum(sizes)} targets ({min(sizes)}-{max(sizes)} per scene)",
+            "ms_per_call": t0.elapsed_time(t1) / steps, "host_synchronisations_per_call": 0,
+            "parity": "tests/test_gpu_matcher.py (scipy.optimize.linear_sum_assignment, the reference's SetCriterion)"}
 
 
 def measure_train_step(dev, rank, world, pool_dev, global_batch=8, steps=4, warmup=2):

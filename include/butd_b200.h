@@ -306,6 +306,24 @@ int bd_attention_tc_set_small_nk(int nk);
  * and `workspace` may be NULL.  on = 0 switches this off (A/B reference: the pack kernel).  Default on. */
 int bd_attention_tc_set_direct(int on);
 
+/* Hungarian matcher on the device (reference: models/losses.py:256-331, which builds the cost matrix in torch,
+ * copies it to the host and calls scipy.optimize.linear_sum_assignment per scene).  Targets of all scenes are
+ * concatenated; scene b owns targets tgt_offset[b] .. tgt_offset[b+1]-1 (tgt_offset: B+1 ints, device).
+ * bd_matcher_cost: cost[t][q] (target-major, Q floats per target) = w_bbox * L1(boxes[b,q], tgt_boxes[t])
+ *   + w_class * -(softmax(logits[b,q]) . positive_map[t])  (labels != NULL: -softmax(...)[labels[t]] instead)
+ *   + w_giou * -GIoU3D(corners(boxes[b,q]), corners(tgt_boxes[t])).  logits (B,Q,C) C <= 512, boxes (B,Q,6) and
+ *   tgt_boxes (T,6) as cx cy cz w h d, positive_map (T, ld_pm >= C).
+ * bd_hungarian: optimal assignment of every scene's targets to distinct queries (targets per scene <= max_targets
+ *   <= Q <= 1024): match_q / match_t [tgt_offset[b] + k], k < T_b, sorted by query index — the (row_ind, col_ind)
+ *   linear_sum_assignment returns for the (Q x T_b) matrix.  A scene whose costs leave no finite augmenting path
+ *   (inf / NaN) gets -1 entries and sets *status (optional, device int) to 1. */
+int bd_matcher_cost(const float *logits, const float *boxes, const float *tgt_boxes,
+                    const float *positive_map, int ld_pm, const long long *labels, const int *tgt_offset,
+                    int B, int Q, int C, float w_class, float w_bbox, float w_giou, float *cost,
+                    bd_stream_t stream);
+int bd_hungarian(const float *cost, const int *tgt_offset, int B, int Q, int max_targets,
+                 long long *match_q, long long *match_t, int *status, bd_stream_t stream);
+
 /* RoBERTa input embeddings (text side, reference call site models/bdetr.py:168 -> transformers
  * RobertaEmbeddings.forward): Y (B*L, D) = LayerNorm(word[ids] + position[pid] + token_type[0]) with
  * pid = pad_idx + running count of non-pad tokens (pad tokens: pad_idx).  ids (B,L) int64; word (vocab,D),
