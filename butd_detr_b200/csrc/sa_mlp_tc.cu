@@ -47,6 +47,36 @@ struct SaMlpParams {
   uint32_t x_bytes;  // bytes of the A-ring / hidden-activation region
 };
 
+// Last layer with the operands SWAPPED (D^T = W2 . H^T: accumulator lane = output channel, accumulator column =
+// grouped row): the max over the nsample rows of a centre is then a thread-local loop over TMEM columns — no
+// cross-lane reduction, no shared tile, no barrier — and a warp writes 32 consecutive channels of one pooled row.
+// Columns [c_begin, c_begin + c_count) of the accumulator at `tacc` (this thread's lane), nsample in {16,32,64,128}.
+__device__ __forceinline__ void pool_swapped(uint32_t tacc, int c_begin, int c_count, int ns, float bias, long long row0,
+                                             int M, float *__restrict__ Y, int ldy, int ch) {
+  float m = -INFINITY;
+  for (int g = 0; g < c_count / 16; g += 2) {
+    uint32_t a0[16], a1[16];
+    tc::tmem_ld16(tacc + c_begin + g * 16, a0);
+    tc::tmem_ld16(tacc + c_begin + (g + 1) * 16, a1);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t(&a)[16] = u ? a1 : a0;
+      float m0 = fmaxf(__uint_as_float(a[0]), __uint_as_float(a[1])), m1 = fmaxf(__uint_as_float(a[2]), __uint_as_float(a[3]));
+      float m2 = fmaxf(__uint_as_float(a[4]), __uint_as_float(a[5])), m3 = fmaxf(__uint_as_float(a[6]), __uint_as_float(a[7]));
+      m0 = fmaxf(m0, fmaxf(__uint_as_float(a[8]), __uint_as_float(a[9]))), m1 = fmaxf(m1, fmaxf(__uint_as_float(a[10]), __uint_as_float(a[11])));
+      m2 = fmaxf(m2, fmaxf(__uint_as_float(a[12]), __uint_as_float(a[13]))), m3 = fmaxf(m3, fmaxf(__uint_as_float(a[14]), __uint_as_float(a[15])));
+      m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+      const int col_end = c_begin + (g + u + 1) * 16;  // columns consumed so far (exclusive)
+      if (col_end % ns == 0) {  // a centre's rows are complete: max_r relu(x_r + b) = relu(max_r x_r + b)
+        const long long orow = (row0 + col_end) / ns - 1;
+        if (orow * ns < M) Y[orow * ldy + ch] = fmaxf(m + bias, 0.f);
+        m = -INFINITY;
+      }
+    }
+  }
+}
+
 template <int PARTS>
 __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kernel(const SaMlpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,6 +93,9 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
   const int n1 = p.L[0].n_chunks;
   const int nmax = max(p.L[0].N, max(p.L[1].N, p.L[2].N));
   const uint32_t ncols = tc::tmem_cols_pow2(nmax);
+  // last layer with swapped operands (pool_swapped): output widths 128 / 256, nsample 16 .. 128 (64 when one
+  // accumulator's columns are split between the two warpgroups)
+  const bool swap2 = p.L[2].BN == SA_BM && p.ns >= 16 && (p.L[2].n_sub == 2 || p.ns <= 64);
 
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), ncols);
   if (tid == 32) {
@@ -106,6 +139,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
       const uint32_t idesc = tc::idesc_ab(PARTS, SA_BM, L.BN);
       const uint32_t w_blk = static_cast<uint32_t>(L.BN) * 128u;
       const int k_total = l == 0 ? p.K1 : p.L[l - 1].N;  // valid K of this layer
+      const bool swapped = l == 2 && swap2;  // D^T = W . H^T (BN = 128 = SA_BM: same instruction shape)
       if (l > 0) {  // hidden activations of the previous layer are in shared memory (and TMEM was drained)
         tc::mbar_wait(tc::smem_u32(&bar_h), (l - 1) & 1);
       }
@@ -128,11 +162,17 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
             for (int sub = 0; sub < L.n_sub; ++sub) {
               const uint32_t d = tmem + sub * L.BN;
               const uint64_t dw_hi = tc::smem_desc_sw128(w0 + sub * w_blk + s * 32);
-              tc::mma_bf16(d, da_hi, dw_hi, idesc, acc);
+              if (swapped) tc::mma_bf16(d, dw_hi, da_hi, idesc, acc);
+              else tc::mma_bf16(d, da_hi, dw_hi, idesc, acc);
               if (PARTS == 2) {
                 const uint64_t dw_lo = tc::smem_desc_sw128(w0 + (L.n_sub + sub) * w_blk + s * 32);
-                tc::mma_bf16(d, da_lo, dw_hi, idesc, 1u);
-                tc::mma_bf16(d, da_hi, dw_lo, idesc, 1u);
+                if (swapped) {
+                  tc::mma_bf16(d, dw_hi, da_lo, idesc, 1u);
+                  tc::mma_bf16(d, dw_lo, da_hi, idesc, 1u);
+                } else {
+                  tc::mma_bf16(d, da_lo, dw_hi, idesc, 1u);
+                  tc::mma_bf16(d, da_hi, dw_lo, idesc, 1u);
+                }
               }
             }
           }
@@ -250,9 +290,9 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
             for (int h8 = 0; h8 < 2; ++h8) {
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(acc[u][h8 * 8 + j]) + bias_s[l][k0 + h8 * 8 + j], 0.f);
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[u][h8 * 8 + j]) + bias_s[l][k0 + h8 * 8 + j];
               uint4 hi, lo;
-              tc::cvt8(PARTS, v, hi, lo);
+              tc::cvt8_relu(PARTS, v, hi, lo);  // ReLU inside the conversion
               const int k = k0 + h8 * 8;
               const uint32_t off = static_cast<uint32_t>(k / KC) * A_PART + tc::sw128_off(r, (k % KC) / 8);
               *reinterpret_cast<uint4 *>(sX + off) = hi;
@@ -264,11 +304,19 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_h));
+      } else if (swap2) {
+        // ---- last layer, swapped operands: this thread's accumulator lane is output channel `ch`
+        const int sub = L.n_sub == 2 ? (warp >> 2) : 0;
+        const int ch = sub * SA_BM + r;
+        const int c_begin = L.n_sub == 2 ? 0 : (warp >> 2) * 64, c_count = L.n_sub == 2 ? SA_BM : 64;
+        pool_swapped(tbase + sub * SA_BM, c_begin, c_count, p.ns, bias_s[l][ch], row0, p.M, p.Y, p.ldy, ch);
       } else {
         // ---- last layer: +bias, ReLU -> shared tile -> max over the nsample rows of each centre,
         //      in column passes of at most 128 (tile = 128 x 132 floats: small enough for two CTAs
         //      per SM in the single-part mode).  The tile reuses the A / W regions: every MMA and
-        //      weight copy has completed.
+        //      weight copy has completed.  (Measured alternative: warp reductions of the accumulators —
+        //      CREDUX.MAX.F32, one per column and warp — are SLOWER here: SA2 +6 %, SA3 / SA4 (half-warp
+        //      masks) +26 %; the reduction instruction is the scarce resource, the tile pass is not.)
         const int PW = min(L.N, 128);  // columns per pass
         const int ldt = PW + 4;
         float *tile = reinterpret_cast<float *>(smem);
@@ -338,6 +386,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
   const int n_tiles = (p.M + SA_BM - 1) / SA_BM;
+  const bool swap2 = N2 == SA_BM;  // last layer with swapped operands: thread-local pooling (pool_swapped); nsample 32 / 64
 
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 128);
   if (tid == 32) {
@@ -383,6 +432,14 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
           for (int s = 0; s < ksteps; ++s) {
             const uint64_t da_hi = tc::smem_desc_sw128(a0 + s * 32), da_lo = tc::smem_desc_sw128(a0 + A_PART + s * 32);
             const uint64_t dw_hi = tc::smem_desc_sw128(w + s * 32), dw_lo = tc::smem_desc_sw128(w + w_lo + s * 32);
+            if (l == 2 && swap2) {  // D^T = W2 . H^T (N2 = 128: same instruction shape)
+              tc::mma_bf16(tmem, dw_hi, da_hi, idesc, s > 0 ? 1u : 0u);
+              if (PARTS == 2) {
+                tc::mma_bf16(tmem, dw_hi, da_lo, idesc, 1u);
+                tc::mma_bf16(tmem, dw_lo, da_hi, idesc, 1u);
+              }
+              continue;
+            }
             tc::mma_bf16(tmem, da_hi, dw_hi, idesc, s > 0 ? 1u : 0u);
             if (PARTS == 2) {
               tc::mma_bf16(tmem, da_lo, dw_hi, idesc, 1u);
@@ -449,9 +506,9 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
             const int k = half * 32 + u * 16 + h8 * 8;
             float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(acc[u][h8 * 8 + j]) + bias_s[l][k + j], 0.f);
+            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(acc[u][h8 * 8 + j]) + bias_s[l][k + j];
             uint4 hi, lo;
-            tc::cvt8(PARTS, o, hi, lo);
+            tc::cvt8_relu(PARTS, o, hi, lo);  // ReLU inside the conversion
             const uint32_t off = tc::sw128_off(row, k / 8);
             *reinterpret_cast<uint4 *>(sX + off) = hi;
             if (PARTS == 2) *reinterpret_cast<uint4 *>(sX + A_PART + off) = lo;
@@ -465,23 +522,28 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
       // ---- last layer: +bias, ReLU, max over the rows of each centre
       tc::mbar_wait(tc::smem_u32(&bar_acc), (3 * it + 2) & 1);
       tc::fence_after_sync();
+      if (swap2) {  // lane = output channel; this warpgroup's 64 accumulator columns = its centre(s)
+        pool_swapped(tbase, half * 64, 64, p.ns, bias_s[2][row], static_cast<long long>(tile) * SA_BM, p.M, p.Y, p.ldy, row);
+        continue;  // (the next tile's layer-1 operand store is ordered after these TMEM reads by its fence)
+      }
       const int ncol = N2 / 2;  // columns of this warpgroup
       for (int g = 0; g < ncol / 16; ++g) {
         uint32_t acc[16];
         tc::tmem_ld16(tbase + half * ncol + g * 16, acc);
         tc::tmem_ld_wait();
+        // max over the warp's 32 rows of the RAW accumulators (CREDUX.MAX.F32), bias and ReLU on the one survivor:
+        // max_r relu(x_r + b) = relu(max_r x_r + b) exactly (fp32 addition is monotonic)
         float mine = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float x = fmaxf(__uint_as_float(acc[j]) + bias_s[2][half * ncol + g * 16 + j], 0.f);
 #ifdef SA1_NO_POOL
-          const unsigned mx = __float_as_uint(x) & 0x7FFFFFFFu;
+          const float mx = __uint_as_float(acc[j]);
 #else
-          const unsigned mx = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(x) & 0x7FFFFFFFu);
+          const float mx = tc::redux_max_f32(__uint_as_float(acc[j]));
 #endif
-          if (lane == j) mine = __uint_as_float(mx);
+          if (lane == j) mine = mx;
         }
-        if (lane < 16) pool_s[warp & 3][half * ncol + g * 16 + lane] = mine;
+        if (lane < 16) pool_s[warp & 3][half * ncol + g * 16 + lane] = fmaxf(mine + bias_s[2][half * ncol + g * 16 + lane], 0.f);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int e = tid; e < per_tile * N2; e += SA_WARPS * 32) {

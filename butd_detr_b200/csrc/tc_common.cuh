@@ -237,6 +237,24 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// same with max(., 0) applied by the conversion (F2FP.RELU): ReLU costs no instruction of its own
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// warp-wide maximum of an fp32 value (CREDUX.MAX.F32, sm_100a): whole warp / the caller's 16-lane half
+__device__ __forceinline__ float redux_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float redux_max_f32_half(float v, int lane) {
+  float r;
+  if (lane < 16) asm volatile("redux.sync.max.f32 %0, %1, 0x0000ffff;" : "=f"(r) : "f"(v));
+  else asm volatile("redux.sync.max.f32 %0, %1, 0xffff0000;" : "=f"(r) : "f"(v));
+  return r;
+}
 // 8 fp32 -> operand chunk(s): parts == 2: bf16 hi + bf16 lo; parts == 1: fp16 (lo untouched)
 __device__ __forceinline__ void cvt8(int parts, const float (&v)[8], uint4 &hi, uint4 &lo) {
   if (parts == 2) {
@@ -244,6 +262,18 @@ __device__ __forceinline__ void cvt8(int parts, const float (&v)[8], uint4 &hi, 
   } else {
     hi.x = pack_f16x2(v[0], v[1]), hi.y = pack_f16x2(v[2], v[3]);
     hi.z = pack_f16x2(v[4], v[5]), hi.w = pack_f16x2(v[6], v[7]);
+  }
+}
+
+// relu(v) -> operand chunk(s)
+__device__ __forceinline__ void cvt8_relu(int parts, const float (&v)[8], uint4 &hi, uint4 &lo) {
+  if (parts == 2) {
+    const float r[8] = {fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f),
+                        fmaxf(v[4], 0.f), fmaxf(v[5], 0.f), fmaxf(v[6], 0.f), fmaxf(v[7], 0.f)};
+    split_bf16x8(r, hi, lo);
+  } else {
+    hi.x = pack_f16x2_relu(v[0], v[1]), hi.y = pack_f16x2_relu(v[2], v[3]);
+    hi.z = pack_f16x2_relu(v[4], v[5]), hi.w = pack_f16x2_relu(v[6], v[7]);
   }
 }
 
