@@ -419,13 +419,18 @@ __global__ void __launch_bounds__(TC_THREADS, (MODE == 0 && EPI != 1) ? 2 : 1) l
           for (int j = 0; j < 16; ++j) {
             float v = __uint_as_float(acc[u][j]) + bias_s[(g + u) * 16 + j];
             if (GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // exact (erf) GELU: RoBERTa's FFN
-            else if (!LN_EPI && p.relu) v = fmaxf(v, 0.f);
+            else if (!LN_EPI && p.relu && !(EPI == 0 && p.y16)) v = fmaxf(v, 0.f);
             o[j] = v;
           }
-          if (EPI == 0 && p.y16) {  // fp16 rows: row stride NC + 8 halfs
+          if (EPI == 0 && p.y16) {  // fp16 rows: row stride NC + 8 halfs; ReLU inside the conversion (F2FP.RELU)
             uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(tile) + r * (NC + 8) + (g + u) * 16);
-            dst[0] = make_uint4(tc::pack_f16x2(o[0], o[1]), tc::pack_f16x2(o[2], o[3]), tc::pack_f16x2(o[4], o[5]), tc::pack_f16x2(o[6], o[7]));
-            dst[1] = make_uint4(tc::pack_f16x2(o[8], o[9]), tc::pack_f16x2(o[10], o[11]), tc::pack_f16x2(o[12], o[13]), tc::pack_f16x2(o[14], o[15]));
+            if (!GELU && p.relu) {
+              dst[0] = make_uint4(tc::pack_f16x2_relu(o[0], o[1]), tc::pack_f16x2_relu(o[2], o[3]), tc::pack_f16x2_relu(o[4], o[5]), tc::pack_f16x2_relu(o[6], o[7]));
+              dst[1] = make_uint4(tc::pack_f16x2_relu(o[8], o[9]), tc::pack_f16x2_relu(o[10], o[11]), tc::pack_f16x2_relu(o[12], o[13]), tc::pack_f16x2_relu(o[14], o[15]));
+            } else {
+              dst[0] = make_uint4(tc::pack_f16x2(o[0], o[1]), tc::pack_f16x2(o[2], o[3]), tc::pack_f16x2(o[4], o[5]), tc::pack_f16x2(o[6], o[7]));
+              dst[1] = make_uint4(tc::pack_f16x2(o[8], o[9]), tc::pack_f16x2(o[10], o[11]), tc::pack_f16x2(o[12], o[13]), tc::pack_f16x2(o[14], o[15]));
+            }
             continue;
           }
           float4 *dst = reinterpret_cast<float4 *>(tile + r * ldt + (g + u) * 16);
