@@ -56,6 +56,7 @@ _SIGNATURES = {
     "bd_linear_ln_tc_h": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _F, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_linear_tc_set_debug": [_P],
     "bd_sa_group_linear_tc": [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bd_sa_mlp_tc_h": [_P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _P],
     "bd_sa_mlp_tc": [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P],
     "bd_linear_pool_tc": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_add_layernorm_f32": [_P, _P, _P, _P, _P, _I, _I, _F, _P],

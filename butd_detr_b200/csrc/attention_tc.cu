@@ -421,6 +421,53 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, unsigned long long ne
   }
 }
 
+// A short last key tile (fewer than 97 keys): both softmax passes over the `nch` 32-key chunks that hold keys only
+// (plain loops, one chunk in flight: these tiles are a small share of the work; the rest of the S / P columns
+// stays stale and the P.V MMAs stop at the same chunk).  Returns the row maximum of the tile through `mx`.
+template <int PARTS>
+__device__ __forceinline__ float softmax_short_max(uint32_t tS, const uint32_t (&vw)[4], int nch) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c < nch) {
+      uint32_t a[32];
+      tc::tmem_ld32(tS + c * 32, a);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if ((vw[c] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(a[i]));
+    }
+  }
+  return mx;
+}
+template <int PARTS>
+__device__ __forceinline__ void softmax_short_exp(uint32_t tS, float neg_m, const uint32_t (&vw)[4], bool dead, int nch) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c < nch) {
+      uint32_t a[32], o[32];
+      tc::tmem_ld32(tS + c * 32, a);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = tc::ex2_approx(__uint_as_float(a[i]) + neg_m), p1 = tc::ex2_approx(__uint_as_float(a[i + 1]) + neg_m);
+        if (dead || !((vw[c] >> i) & 1u)) p0 = 0.f;
+        if (dead || !((vw[c] >> (i + 1)) & 1u)) p1 = 0.f;
+        if (PARTS == 2) tc::split_bf16x2(p0, p1, o[i >> 1], o[16 + (i >> 1)]);
+        else o[i >> 1] = tc::pack_f16x2(p0, p1);
+      }
+      if (PARTS == 2) {
+        tc::tmem_st32(tS + c * 32, o);
+      } else {
+        uint32_t o16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o16[i] = o[i];
+        tc::tmem_st16(tS + c * 32, o16);
+      }
+    }
+  }
+}
+
 // DIRECT (fp16 K / V rows in HBM, PARTS == 1): the loader fetches each head's K tile [128 keys x 64 columns]
 // and V tile [128 keys x 64 columns] with ONE tensor copy each from the projection output.  A tensor copy must
 // start on a 16-byte boundary and a head starts at byte 72 h, so odd heads start 4 columns early (SHIFT = 4):
@@ -503,8 +550,7 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
     __syncwarp();
   } else if (warp == 1) {
     // -------------------------------------------------------------------------- MMA issuer
-    const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, WS_BK),
-                   idesc_o = tc::idesc_ab(PARTS, AT_BM, NV) | (DIRECT ? tc::idesc_b_mn : 0u),
+    const uint32_t idesc_o = tc::idesc_ab(PARTS, AT_BM, NV) | (DIRECT ? tc::idesc_b_mn : 0u),
                    idesc_1 = tc::idesc_ab(PARTS, AT_BM, 16);
     tc::mbar_wait(tc::smem_u32(&bar_q), 0);
     for (int j = 0; j <= nk; ++j) {  // iteration j: P.V of key tile j-1, then Q.K^T of key tile j
@@ -517,9 +563,13 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
           tc::fence_after_sync();
           if (tc::elect_one()) {
             const uint32_t va = tc::smem_u32(sV + st * V_TILE);
+            // a short last key tile: only the 32-key chunks that hold keys were exponentiated (the rest of the
+            // S / P columns are stale), so P.V stops there
+            const int ksteps = 2 * ((min(WS_BK, p.Lk - jj * WS_BK) + 31) >> 5);
             if (!(p.dbg & 2))
 #pragma unroll
             for (int s = 0; s < WS_BK / 16; ++s) {  // 16 keys per step: 8 TMEM columns of packed bf16 pairs
+              if (s >= ksteps) break;
               const uint32_t a_hi = tS + (s >> 1) * 32 + (s & 1) * 8;
               const uint64_t dv = DIRECT ? tc::smem_desc_sw128_mn(va + s * 2048)  // 16 keys = two 8-row swizzle atoms
                                          : tc::smem_desc_sw128(va + (s >> 2) * V_BLK + (s & 3) * 32);
@@ -543,6 +593,8 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
           tc::fence_after_sync();
           if (tc::elect_one()) {
             const uint32_t q = tc::smem_u32(sQ + t * Q_TILE), k = tc::smem_u32(sK + st * K_TILE);
+            // scores only for the 32-key chunks of this tile that hold keys (N = 32, 64, 96 or 128)
+            const uint32_t idesc_s = tc::idesc_ab(PARTS, AT_BM, 32 * ((min(WS_BK, p.Lk - j * WS_BK) + 31) >> 5));
             if (!(p.dbg & 4))
 #pragma unroll
             for (int s = 0; s < NV / 16; ++s) {  // head_dim 36 -> 48: three K=16 steps (the tile is padded to 64)
@@ -649,8 +701,11 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
         continue;
       }
 
-      // ---- pass 1: row maximum
+      // ---- pass 1: row maximum (a short last tile: only the 32-key chunks that hold keys)
+      const int nch = (min(WS_BK, p.Lk - k0) + 31) >> 5;
       float mx = -INFINITY;
+      if (nch < 4) mx = softmax_short_max<PARTS>(tS, vw, nch);
+      else
 #pragma unroll
       for (int c = 0; c < 4; c += 2) {
         uint32_t a0[32], a1[32];
@@ -684,6 +739,8 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
       // ---- pass 2: p = 2^(s - m), split into bf16 hi / lo, stored over the scores in place
       if (all_valid) {
         softmax_pass2<PARTS, false>(tS, neg_m2, vw, dead);
+      } else if (nch < 4) {
+        softmax_short_exp<PARTS>(tS, neg_m, vw, dead, nch);
       } else {
         softmax_pass2<PARTS, true>(tS, neg_m2, vw, dead);
       }

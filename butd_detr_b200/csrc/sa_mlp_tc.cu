@@ -43,6 +43,11 @@ struct SaMlpParams {
   int M, K1, split;
   float inv_r;
   SaLayer L[3];
+  // 16-bit feature rows between the levels (fp16 mode): feat16 = `feat` points at fp16 rows (ldf in halfs, C % 8 == 0:
+  // a 16-byte chunk of 8 features is copied into the operand tile as it is — no conversion, half the gather
+  // bytes); Y16 = the pooled rows are ALSO written as fp16 (the next level's gather source)
+  int feat16, ldy16;
+  __half *Y16;
   uint32_t w_stage;  // bytes of one weight-ring stage (largest chunk)
   uint32_t x_bytes;  // bytes of the A-ring / hidden-activation region
 };
@@ -52,7 +57,8 @@ struct SaMlpParams {
 // cross-lane reduction, no shared tile, no barrier — and a warp writes 32 consecutive channels of one pooled row.
 // Columns [c_begin, c_begin + c_count) of the accumulator at `tacc` (this thread's lane), nsample in {16,32,64,128}.
 __device__ __forceinline__ void pool_swapped(uint32_t tacc, int c_begin, int c_count, int ns, float bias, long long row0,
-                                             int M, float *__restrict__ Y, int ldy, int ch) {
+                                             int M, float *__restrict__ Y, int ldy, int ch, __half *__restrict__ Y16 = nullptr,
+                                             int ldy16 = 0) {
   float m = -INFINITY;
   for (int g = 0; g < c_count / 16; g += 2) {
     uint32_t a0[16], a1[16];
@@ -70,7 +76,11 @@ __device__ __forceinline__ void pool_swapped(uint32_t tacc, int c_begin, int c_c
       const int col_end = c_begin + (g + u + 1) * 16;  // columns consumed so far (exclusive)
       if (col_end % ns == 0) {  // a centre's rows are complete: max_r relu(x_r + b) = relu(max_r x_r + b)
         const long long orow = (row0 + col_end) / ns - 1;
-        if (orow * ns < M) Y[orow * ldy + ch] = fmaxf(m + bias, 0.f);
+        if (orow * ns < M) {
+          const float o = fmaxf(m + bias, 0.f);
+          Y[orow * ldy + ch] = o;
+          if (Y16) Y16[orow * ldy16 + ch] = __float2half_rn(fminf(o, 65504.f));
+        }
         m = -INFINITY;
       }
     }
@@ -212,7 +222,10 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
         const int k0 = c * KC + k_off[it];
         const bool ok = row_ok[it] && k0 < p.K1;
         const float *f = p.feat + f_off[it];
-        if (ok && k0 + 8 <= p.C && feat_vec) {  // chunk entirely inside the feature row
+        const __half *fh = reinterpret_cast<const __half *>(p.feat) + f_off[it];
+        if (p.feat16 && k0 + 8 <= p.C) {  // 8 fp16 features: one 16-byte load, kept as bits (zeros for a dead row)
+          ra[it][0] = ok ? __ldg(reinterpret_cast<const float4 *>(fh + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (ok && k0 + 8 <= p.C && feat_vec) {  // chunk entirely inside the feature row
           ra[it][0] = __ldg(reinterpret_cast<const float4 *>(f + k0));
           ra[it][1] = __ldg(reinterpret_cast<const float4 *>(f + k0) + 1);
         } else {  // chunk straddles features / relative xyz / padding
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
           for (int i = 0; i < 8; ++i) {
             const int k = k0 + i;
             float x = 0.f;
-            if (ok && k < p.C) x = __ldg(f + k);
+            if (ok && k < p.C) x = p.feat16 ? __half2float(fh[k]) : __ldg(f + k);
             else if (ok && k < p.C + 3)
               x = __fmul_rn(__fsub_rn(__ldg(p.xyz + x_off[it] + (k - p.C)), __ldg(p.cen + c_off[it] + (k - p.C))), p.inv_r);
             v[i] = x;
@@ -244,7 +257,19 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
 #pragma unroll
       for (int it = 0; it < SA_ITEMS; ++it) {
         if (k_off[it] >= kend) continue;
-        const float v[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w, ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
+        float v[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w, ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
+        if (p.feat16 && c * KC + k_off[it] + 8 <= p.C) {  // the registers hold 8 fp16 features as loaded
+          if (PARTS == 1) {  // already the operand format
+            *reinterpret_cast<float4 *>(sA + s_off[it]) = ra[it][0];
+            continue;
+          }
+          const __half2 *h2 = reinterpret_cast<const __half2 *>(&ra[it][0]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f2 = __half22float2(h2[i]);
+            v[2 * i] = f2.x, v[2 * i + 1] = f2.y;
+          }
+        }
         uint4 hi, lo;
         tc::cvt8(PARTS, v, hi, lo);
         *reinterpret_cast<uint4 *>(sA + s_off[it]) = hi;
@@ -309,7 +334,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
         const int sub = L.n_sub == 2 ? (warp >> 2) : 0;
         const int ch = sub * SA_BM + r;
         const int c_begin = L.n_sub == 2 ? 0 : (warp >> 2) * 64, c_count = L.n_sub == 2 ? SA_BM : 64;
-        pool_swapped(tbase + sub * SA_BM, c_begin, c_count, p.ns, bias_s[l][ch], row0, p.M, p.Y, p.ldy, ch);
+        pool_swapped(tbase + sub * SA_BM, c_begin, c_count, p.ns, bias_s[l][ch], row0, p.M, p.Y, p.ldy, ch, p.Y16, p.ldy16);
       } else {
         // ---- last layer: +bias, ReLU -> shared tile -> max over the nsample rows of each centre,
         //      in column passes of at most 128 (tile = 128 x 132 floats: small enough for two CTAs
@@ -351,6 +376,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 2 : 1) sa_mlp_tc_kern
             float mx = tt[0];
             for (int q = 1; q < p.ns; ++q) mx = fmaxf(mx, tt[q * ldt]);
             p.Y[orow * p.ldy + c0 + col] = mx;
+            if (p.Y16) p.Y16[orow * p.ldy16 + c0 + col] = __float2half_rn(fminf(mx, 65504.f));
           }
           if (c0 + PW < L.N) asm volatile("bar.sync 1, 256;" ::: "memory");  // tile free for the next pass
         }
@@ -523,7 +549,8 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
       tc::mbar_wait(tc::smem_u32(&bar_acc), (3 * it + 2) & 1);
       tc::fence_after_sync();
       if (swap2) {  // lane = output channel; this warpgroup's 64 accumulator columns = its centre(s)
-        pool_swapped(tbase, half * 64, 64, p.ns, bias_s[2][row], static_cast<long long>(tile) * SA_BM, p.M, p.Y, p.ldy, row);
+        pool_swapped(tbase, half * 64, 64, p.ns, bias_s[2][row], static_cast<long long>(tile) * SA_BM, p.M, p.Y, p.ldy, row,
+                     p.Y16, p.ldy16);
         continue;  // (the next tile's layer-1 operand store is ordered after these TMEM reads by its fence)
       }
       const int ncol = N2 / 2;  // columns of this warpgroup
@@ -554,6 +581,7 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
           float mx = pool_s[w0][col];
           if (p.ns == 64) mx = fmaxf(mx, pool_s[w0 + 1][col]);
           p.Y[orow * p.ldy + col] = mx;
+          if (p.Y16) p.Y16[orow * p.ldy16 + col] = __float2half_rn(fminf(mx, 65504.f));
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // pool_s free again
@@ -570,10 +598,37 @@ __global__ void __launch_bounds__(SA_THREADS, PARTS == 1 ? 3 : 2) sa_mlp_residen
 // feats (B,n,C) token-major rows (ld_feats), xyz (B,n,3) rows (ld_xyz), new_xyz (B,m,3) centres.
 // Layer l: packed weights Wp[l] (pack_weight_tc, full_rows tiling: BN[l] x n_sub[l] = N[l]),
 // bias[l]; layer 1's K columns ordered [features | xyz | 0].  Y (B*m, N[2]) pooled rows.
+static int sa_mlp_tc_impl(const int *idx, const float *feats, int ld_feats, int C, const float *xyz, int ld_xyz,
+                          const float *new_xyz, int B, int n, int m, int ns, float radius, const void *Wp0,
+                          const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
+                          const float *b2, int N2, float *Y, int ldy, int split, int feats_half, void *Y16, int ldy16,
+                          bd_stream_t stream);
 extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, int C, const float *xyz, int ld_xyz,
                             const float *new_xyz, int B, int n, int m, int ns, float radius, const void *Wp0,
                             const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
                             const float *b2, int N2, float *Y, int ldy, int split, bd_stream_t stream) {
+  return sa_mlp_tc_impl(idx, feats, ld_feats, C, xyz, ld_xyz, new_xyz, B, n, m, ns, radius, Wp0, b0, N0, Wp1, b1, N1, Wp2, b2,
+                        N2, Y, ldy, split, 0, nullptr, 0, stream);
+}
+// bd_sa_mlp_tc with 16-bit feature rows between the levels: feats_half != 0 -> `feats` are fp16 rows (ld_feats in
+// halfs, C % 8 == 0, ld_feats % 8 == 0, 16-byte aligned); Y16 != NULL -> the pooled rows are also written as fp16
+// (ldy16 halfs per row).  Same values: the fp32 path rounds the gathered features to the operand format anyway.
+extern "C" int bd_sa_mlp_tc_h(const int *idx, const void *feats, int ld_feats, int C, int feats_half, const float *xyz,
+                              int ld_xyz, const float *new_xyz, int B, int n, int m, int ns, float radius, const void *Wp0,
+                              const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
+                              const float *b2, int N2, float *Y, int ldy, void *Y16, int ldy16, int split,
+                              bd_stream_t stream) {
+  BD_REQUIRE(!feats_half || (C > 0 && C % 8 == 0 && ld_feats % 8 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0),
+             "bd_sa_mlp_tc_h: fp16 feature rows need C % 8 == 0, ld_feats % 8 == 0 and 16-byte alignment");
+  BD_REQUIRE(!Y16 || ldy16 >= N2, "bd_sa_mlp_tc_h: ldy16 < N2");
+  return sa_mlp_tc_impl(idx, static_cast<const float *>(feats), ld_feats, C, xyz, ld_xyz, new_xyz, B, n, m, ns, radius, Wp0, b0,
+                        N0, Wp1, b1, N1, Wp2, b2, N2, Y, ldy, split, feats_half, Y16, ldy16, stream);
+}
+static int sa_mlp_tc_impl(const int *idx, const float *feats, int ld_feats, int C, const float *xyz, int ld_xyz,
+                          const float *new_xyz, int B, int n, int m, int ns, float radius, const void *Wp0,
+                          const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
+                          const float *b2, int N2, float *Y, int ldy, int split, int feats_half, void *Y16, int ldy16,
+                          bd_stream_t stream) {
   BD_REQUIRE(idx && xyz && new_xyz && Wp0 && Wp1 && Wp2 && Y && (feats || C == 0), "bd_sa_mlp_tc: null pointer");
   BD_REQUIRE(B > 0 && n > 0 && m > 0 && ns > 0 && C >= 0 && ld_xyz >= 3 && ld_feats >= C && ldy >= N2,
              "bd_sa_mlp_tc: bad sizes");
@@ -587,6 +642,7 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
   p.idx = idx, p.feat = feats ? feats : xyz, p.xyz = xyz, p.cen = new_xyz, p.Y = Y;
   p.ldf = ld_feats, p.ldx = ld_xyz, p.C = C, p.ns = ns, p.n = n, p.m = m, p.ldy = ldy;
   p.M = B * m * ns, p.K1 = (C + 3 + 7) / 8 * 8, p.split = split, p.inv_r = 1.0f / radius;
+  p.feat16 = feats_half ? 1 : 0, p.Y16 = static_cast<__half *>(Y16), p.ldy16 = ldy16;
   const void *W[3] = {Wp0, Wp1, Wp2};
   const float *bs[3] = {b0, b1, b2};
   const int N[3] = {N0, N1, N2};
@@ -601,7 +657,7 @@ extern "C" int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, in
     if (chunk > w_stage) w_stage = chunk;
   }
   p.w_stage = w_stage;
-  if (p.K1 <= 16 && N0 == 64 && N1 == 64 && N2 <= 128 && (ns == 32 || ns == 64)) {
+  if (p.K1 <= 16 && N0 == 64 && N1 == 64 && N2 <= 128 && (ns == 32 || ns == 64) && !feats_half) {
     // resident-weights persistent kernel (SA1)
     const size_t smem_r = static_cast<size_t>(parts) * (2 * 64 + N2 + SA_BM) * 128 + 1024;
     static bd::PerDeviceOnce configured_r;  // function attributes are per device

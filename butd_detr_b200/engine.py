@@ -579,6 +579,20 @@ class ForwardEngine:
             self._tc[key] = [pack_weight_tc(w, self.split, full_rows=True)[0] for w in (Wr, Ws[1][0], Ws[2][0])]
         Wp = self._tc[key]
         out = self._empty(B, m, N[2])
+        if self.half:
+            # 16-bit feature rows between the levels: gather the previous level's fp16 copy (half the bytes, no
+            # conversion) and leave an fp16 copy of this level's pooled rows for the next one
+            f16 = self._shadow.get(feats.data_ptr()) if torch.is_tensor(feats) else None
+            use16 = f16 is not None and C % 8 == 0 and f16.shape[-1] == C
+            out16 = self._empty(B, m, N[2], dtype=torch.float16) if name != SA_CFG[-1][0] else None
+            src = f16 if use16 else feats
+            _lib.call("bd_sa_mlp_tc_h", idx.data_ptr(), src.data_ptr(), C if use16 else ld_feats, C, int(use16),
+                      xyz.data_ptr(), ld_xyz, new_xyz.data_ptr(), B, n, m, ns, float(radius), Wp[0].data_ptr(),
+                      Ws[0][1].data_ptr(), N[0], Wp[1].data_ptr(), Ws[1][1].data_ptr(), N[1], Wp[2].data_ptr(),
+                      Ws[2][1].data_ptr(), N[2], out.data_ptr(), N[2], _lib.ptr(out16), N[2], self.split)
+            if out16 is not None:
+                self._shadow[out.data_ptr()] = out16
+            return out
         _lib.call("bd_sa_mlp_tc", idx.data_ptr(), feats.data_ptr(), ld_feats, C, xyz.data_ptr(), ld_xyz,
                   new_xyz.data_ptr(), B, n, m, ns, float(radius), Wp[0].data_ptr(), Ws[0][1].data_ptr(), N[0],
                   Wp[1].data_ptr(), Ws[1][1].data_ptr(), N[1], Wp[2].data_ptr(), Ws[2][1].data_ptr(), N[2],

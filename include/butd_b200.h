@@ -208,6 +208,15 @@ int bd_sa_mlp_tc(const int *idx, const float *feats, int ld_feats, int C, const 
                  const float *new_xyz, int B, int n, int m, int ns, float radius, const void *Wp0,
                  const float *b0, int N0, const void *Wp1, const float *b1, int N1, const void *Wp2,
                  const float *b2, int N2, float *Y, int ldy, int split, bd_stream_t stream);
+/* bd_sa_mlp_tc with 16-bit feature rows between the levels (fp16 mode): feats_half != 0 -> `feats` are fp16 rows
+ * (ld_feats in halfs; C % 8 == 0, ld_feats % 8 == 0, 16-byte aligned) that are copied into the operand tiles as
+ * they are; Y16 != NULL -> the pooled rows are ALSO written as fp16 (ldy16 halfs per row), the gather source of the
+ * next level.  Same values as bd_sa_mlp_tc in the fp16 mode (it rounds the gathered features to fp16 itself). */
+int bd_sa_mlp_tc_h(const int *idx, const void *feats, int ld_feats, int C, int feats_half, const float *xyz,
+                   int ld_xyz, const float *new_xyz, int B, int n, int m, int ns, float radius,
+                   const void *Wp0, const float *b0, int N0, const void *Wp1, const float *b1, int N1,
+                   const void *Wp2, const float *b2, int N2, float *Y, int ldy, void *Y16, int ldy16,
+                   int split, bd_stream_t stream);
 
 /* 16-bit activation variants of bd_linear_tc / bd_linear_ln_tc (fp16 operand mode; an fp32 A2 may be
  * added to an fp32 A as in bd_linear_tc): a_half = A

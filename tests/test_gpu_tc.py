@@ -155,6 +155,27 @@ def test_sa_mlp_tc(cuda_lib, B, n, m, ns, C, widths, split):
     want = x.max(2).values.reshape(B * m, -1).float()
     tol = 1e-2 if split == 1 else 2e-4
     torch.testing.assert_close(out, want, rtol=tol, atol=tol)
+    if C % 8 == 0:
+        # 16-bit feature rows between the levels (bd_sa_mlp_tc_h): fp16 gather source + fp16 copy of the pooled rows;
+        # in the fp16 mode the result must be the SAME bits (the fp32 entry rounds the features to fp16 itself)
+        f16 = feats.half().contiguous()
+        xyz_c = xyz.contiguous()
+        src32 = f16.float() if split == 1 else feats.contiguous()
+        ref = torch.full_like(out, float("nan"))
+        cuda_lib.call("bd_sa_mlp_tc", idx.data_ptr(), src32.contiguous().data_ptr(), C, C, xyz_c.data_ptr(), 3, new_xyz.data_ptr(),
+                      B, n, m, ns, radius, Wp[0].data_ptr(), bs[0].data_ptr(), widths[0], Wp[1].data_ptr(), bs[1].data_ptr(),
+                      widths[1], Wp[2].data_ptr(), bs[2].data_ptr(), widths[2], ref.data_ptr(), widths[2], split)
+        out2 = torch.full_like(out, float("nan"))
+        out16 = torch.full((B * m, widths[2]), float("nan"), device="cuda", dtype=torch.float16)
+        cuda_lib.call("bd_sa_mlp_tc_h", idx.data_ptr(), f16.data_ptr(), C, C, 1, xyz_c.data_ptr(), 3, new_xyz.data_ptr(),
+                      B, n, m, ns, radius, Wp[0].data_ptr(), bs[0].data_ptr(), widths[0], Wp[1].data_ptr(), bs[1].data_ptr(),
+                      widths[1], Wp[2].data_ptr(), bs[2].data_ptr(), widths[2], out2.data_ptr(), widths[2], out16.data_ptr(),
+                      widths[2], split)
+        if split == 1:
+            assert torch.equal(out2, ref)
+        else:
+            torch.testing.assert_close(out2, ref, rtol=5e-3, atol=5e-3)  # fp16-rounded features vs fp32 features
+        assert torch.equal(out16, out2.half())
 
 
 @pytest.mark.parametrize("split", [1, 3])
