@@ -49,6 +49,7 @@ _SIGNATURES = {
     "bd_group_rows": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P],
     "bd_maxpool_rows": [_P, _I, _I, _I, _P, _P],
     "bd_fp_interp_concat": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "bd_fp_interp_concat_h": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "bd_linear_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "bd_linear_tc": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_linear_ln_tc": [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -6,6 +6,8 @@
 // single SM of 148 at B = 1.  Here every op is decomposed over (scene, centre/row) so the
 // grid covers the machine, global reads are coalesced (token-major rows) and the candidate
 // points of a ball query are staged through shared memory once per CTA.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -260,6 +262,52 @@ __global__ void fp_interp_concat_kernel(const float *__restrict__ dist2, const i
   out[e] = __fmaf_rn(p2, w2, __fmaf_rn(p0, w0, __fmul_rn(p1, w1)));
 }
 
+// Same operator, one WARP per output row (C1 % 4 == 0, C2 % 4 == 0): the three interpolation weights are computed
+// once per row (the element-per-thread kernel above recomputes 3 square roots and 4 divisions for each of the
+// C1 + C2 elements), features move as 16-byte vectors, and the row can be written as fp16 (HALF: the operand
+// format of the linear layer that reads it next; same fp32 value, rounded once).
+template <bool HALF>
+__global__ void __launch_bounds__(256)
+fp_interp_concat_rows_kernel(const float *__restrict__ dist2, const int *__restrict__ idx,
+                             const float *__restrict__ known_feats, int C2, const float *__restrict__ unknown_feats, int C1,
+                             int n, int m, void *__restrict__ out, long long rows) {
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const long long b = r / n;
+  const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + r * 3 + 0)), 1e-8f));
+  const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + r * 3 + 1)), 1e-8f));
+  const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + r * 3 + 2)), 1e-8f));
+  const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+  const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+  const float *kf = known_feats + b * m * C2;
+  const float4 *k0 = reinterpret_cast<const float4 *>(kf + static_cast<long long>(__ldg(idx + r * 3 + 0)) * C2);
+  const float4 *k1 = reinterpret_cast<const float4 *>(kf + static_cast<long long>(__ldg(idx + r * 3 + 1)) * C2);
+  const float4 *k2 = reinterpret_cast<const float4 *>(kf + static_cast<long long>(__ldg(idx + r * 3 + 2)) * C2);
+  const float4 *uf = reinterpret_cast<const float4 *>(unknown_feats + r * C1);
+  const int W = C1 + C2;
+  for (int v = lane; v < W / 4; v += 32) {
+    float4 o;
+    if (v < C2 / 4) {
+      const float4 p0 = __ldg(k0 + v), p1 = __ldg(k1 + v), p2 = __ldg(k2 + v);
+      o.x = __fmaf_rn(p2.x, w2, __fmaf_rn(p0.x, w0, __fmul_rn(p1.x, w1)));
+      o.y = __fmaf_rn(p2.y, w2, __fmaf_rn(p0.y, w0, __fmul_rn(p1.y, w1)));
+      o.z = __fmaf_rn(p2.z, w2, __fmaf_rn(p0.z, w0, __fmul_rn(p1.z, w1)));
+      o.w = __fmaf_rn(p2.w, w2, __fmaf_rn(p0.w, w0, __fmul_rn(p1.w, w1)));
+    } else {
+      o = __ldg(uf + (v - C2 / 4));
+    }
+    if (HALF) {
+      const __half2 h0 = __floats2half2_rn(fminf(fmaxf(o.x, -65504.f), 65504.f), fminf(fmaxf(o.y, -65504.f), 65504.f));
+      const __half2 h1 = __floats2half2_rn(fminf(fmaxf(o.z, -65504.f), 65504.f), fminf(fmaxf(o.w, -65504.f), 65504.f));
+      reinterpret_cast<uint2 *>(static_cast<__half *>(out) + r * W)[v] =
+          make_uint2(*reinterpret_cast<const unsigned *>(&h0), *reinterpret_cast<const unsigned *>(&h1));
+    } else {
+      reinterpret_cast<float4 *>(static_cast<float *>(out) + r * W)[v] = o;
+    }
+  }
+}
+
 __global__ void transpose_rows_kernel(const float *__restrict__ in, int n, int C, float *__restrict__ out) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -406,15 +454,40 @@ int bd_maxpool_rows(const float *in, int rows_out, int ns, int C, float *out, bd
   return BD_OK;
 }
 
-int bd_fp_interp_concat(const float *dist2, const int *idx, const float *known_feats, int C2,
-                        const float *unknown_feats, int C1, int B, int n, int m, float *out, bd_stream_t stream) {
+static int fp_interp_concat_impl(const float *dist2, const int *idx, const float *known_feats, int C2,
+                                 const float *unknown_feats, int C1, int B, int n, int m, void *out, int out_half,
+                                 bd_stream_t stream) {
   BD_REQUIRE(dist2 && idx && known_feats && out && (unknown_feats || C1 == 0), "bd_fp_interp_concat: null pointer");
   BD_REQUIRE(B > 0 && n > 0 && m > 0 && C2 > 0 && C1 >= 0, "bd_fp_interp_concat: bad sizes");
-  const long long total = static_cast<long long>(B) * n * (C1 + C2);
-  fp_interp_concat_kernel<<<grid1d(total, 256), 256, 0, bd::as_stream(stream)>>>(dist2, idx, known_feats, C2,
-                                                                                unknown_feats, C1, n, m, out, total);
+  const bool vec = C1 % 4 == 0 && C2 % 4 == 0 && (reinterpret_cast<uintptr_t>(known_feats) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(unknown_feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  BD_REQUIRE(!out_half || vec, "bd_fp_interp_concat_h: fp16 rows need C1 % 4 == 0, C2 % 4 == 0 and 16-byte aligned tensors");
+  if (vec) {
+    const long long rows = static_cast<long long>(B) * n;
+    if (out_half)
+      fp_interp_concat_rows_kernel<true><<<grid1d(rows, 8), 256, 0, bd::as_stream(stream)>>>(dist2, idx, known_feats, C2,
+                                                                                           unknown_feats, C1, n, m, out, rows);
+    else
+      fp_interp_concat_rows_kernel<false><<<grid1d(rows, 8), 256, 0, bd::as_stream(stream)>>>(dist2, idx, known_feats, C2,
+                                                                                            unknown_feats, C1, n, m, out, rows);
+  } else {
+    const long long total = static_cast<long long>(B) * n * (C1 + C2);
+    fp_interp_concat_kernel<<<grid1d(total, 256), 256, 0, bd::as_stream(stream)>>>(dist2, idx, known_feats, C2, unknown_feats,
+                                                                                  C1, n, m, static_cast<float *>(out), total);
+  }
   BD_CHECK_LAUNCH("bd_fp_interp_concat");
   return BD_OK;
+}
+
+int bd_fp_interp_concat(const float *dist2, const int *idx, const float *known_feats, int C2,
+                        const float *unknown_feats, int C1, int B, int n, int m, float *out, bd_stream_t stream) {
+  return fp_interp_concat_impl(dist2, idx, known_feats, C2, unknown_feats, C1, B, n, m, out, 0, stream);
+}
+
+int bd_fp_interp_concat_h(const float *dist2, const int *idx, const float *known_feats, int C2,
+                          const float *unknown_feats, int C1, int B, int n, int m, void *out, int out_half,
+                          bd_stream_t stream) {
+  return fp_interp_concat_impl(dist2, idx, known_feats, C2, unknown_feats, C1, B, n, m, out, out_half, stream);
 }
 
 int bd_transpose_rows(const float *in, int B, int n, int C, float *out, bd_stream_t stream) {

@@ -643,10 +643,15 @@ class ForwardEngine:
         idx = self._empty(B, n, 3, dtype=torch.int32)
         _lib.call("bd_three_nn", unknown.data_ptr(), known.data_ptr(), B, n, m, dist2.data_ptr(), idx.data_ptr())
         C2, C1 = known_feats.shape[-1], unknown_feats.shape[-1]
-        x = self._empty(B * n, C1 + C2)
-        _lib.call("bd_fp_interp_concat", dist2.data_ptr(), idx.data_ptr(), known_feats.data_ptr(), C2,
-                  unknown_feats.data_ptr(), C1, B, n, m, x.data_ptr())
-        h = self.lin(x, name + ".0", relu=True)
+        if self.half and C1 % 8 == 0 and C2 % 8 == 0:  # fp16 rows: the operand of the first layer; fp16 hidden layer
+            x = self._empty(B * n, C1 + C2, dtype=torch.float16)
+            _lib.call("bd_fp_interp_concat_h", dist2.data_ptr(), idx.data_ptr(), known_feats.data_ptr(), C2,
+                      unknown_feats.data_ptr(), C1, B, n, m, x.data_ptr(), 1)
+        else:
+            x = self._empty(B * n, C1 + C2)
+            _lib.call("bd_fp_interp_concat", dist2.data_ptr(), idx.data_ptr(), known_feats.data_ptr(), C2,
+                      unknown_feats.data_ptr(), C1, B, n, m, x.data_ptr())
+        h = self.lin(x, name + ".0", relu=True, half_out=True)
         return self.lin(h, name + ".1", relu=True).view(B, n, -1)
 
     def backbone(self, pc, ep):

@@ -156,6 +156,12 @@ int bd_maxpool_rows(const float *in, int rows_out, int ns, int C, float *out, bd
 int bd_fp_interp_concat(const float *dist2, const int *idx, const float *known_feats, int C2,
                         const float *unknown_feats, int C1, int B, int n, int m, float *out,
                         bd_stream_t stream);
+/* Same with the row format chosen by the caller: out_half != 0 writes fp16 rows (B*n, C2+C1) — the operand of the
+ * linear layer that follows (C1 % 4 == 0, C2 % 4 == 0, 16-byte aligned tensors); out_half = 0 is
+ * bd_fp_interp_concat. */
+int bd_fp_interp_concat_h(const float *dist2, const int *idx, const float *known_feats, int C2,
+                          const float *unknown_feats, int C1, int B, int n, int m, void *out,
+                          int out_half, bd_stream_t stream);
 
 /* Y = act( (A [+ A2]) · Wᵀ + bias ) : A (M,K) lda, A2 optional same shape (lda2), W (N,K)
  * row-major (torch Linear / 1x1-conv weight, BatchNorm folded by the host), bias (N) or NULL,

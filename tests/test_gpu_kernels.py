@@ -173,3 +173,28 @@ def test_group_maxpool_fp_rows_match_oracle(cuda_lib, oracle_lib):
     cuda_lib.call("bd_fp_interp_concat", d2_d.data_ptr(), i3_d.data_ptr(), kf_d.data_ptr(), 9, uf_d.data_ptr(), 5,
                   2, 512, 256, x.data_ptr())
     torch.testing.assert_close(x.view(2, 512, 14).transpose(1, 2).cpu(), want, rtol=1e-6, atol=1e-6)
+
+
+def test_fp_interp_concat_rows_kernel_equals_the_element_kernel(cuda_lib, oracle_lib):
+    """Channel counts that are multiples of 4 take the warp-per-row kernel (weights once per row, 16-byte vectors):
+    the fp32 rows must equal the oracle's three_interpolate + concat bit for bit (same operation order), the fp16
+    rows (bd_fp_interp_concat_h) must be those values rounded once."""
+    from pointops_cases import cloud
+    g = torch.Generator().manual_seed(4)
+    B, n, m, C2, C1 = 3, 300, 77, 24, 16
+    unknown, known = cloud(5, n, "room", B), cloud(6, m, "room", B)
+    kf, uf = torch.randn(B, C2, m, generator=g), torch.randn(B, C1, n, generator=g)
+    d2, i3 = oracle_lib.three_nn(unknown, known)
+    rec = 1.0 / (torch.sqrt(d2) + 1e-8)
+    w = (rec / rec.sum(2, keepdim=True)).contiguous()
+    want = torch.cat([oracle_lib.three_interpolate(kf, i3, w), uf], 1).transpose(1, 2).contiguous()  # (B, n, C2+C1)
+    d2_d, i3_d = d2.cuda(), i3.cuda()
+    kf_d, uf_d = kf.transpose(1, 2).contiguous().cuda(), uf.transpose(1, 2).contiguous().cuda()
+    x = torch.full((B * n, C2 + C1), float("nan"), device="cuda")
+    cuda_lib.call("bd_fp_interp_concat", d2_d.data_ptr(), i3_d.data_ptr(), kf_d.data_ptr(), C2, uf_d.data_ptr(), C1, B, n, m,
+                  x.data_ptr())
+    torch.testing.assert_close(x.view(B, n, -1).cpu(), want, rtol=1e-6, atol=1e-6)
+    x16 = torch.full((B * n, C2 + C1), float("nan"), device="cuda", dtype=torch.float16)
+    cuda_lib.call("bd_fp_interp_concat_h", d2_d.data_ptr(), i3_d.data_ptr(), kf_d.data_ptr(), C2, uf_d.data_ptr(), C1, B, n, m,
+                  x16.data_ptr(), 1)
+    assert torch.equal(x16, x.half())
