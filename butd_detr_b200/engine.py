@@ -43,7 +43,7 @@ SA_CFG = (  # models/backbone_module.py:44-78
     ("sa3", 512, 0.8, 16),
     ("sa4", 256, 1.2, 16),
 )
-GRID_BALL_QUERY_MIN_POINTS = 8192
+GRID_BALL_QUERY_MIN_POINTS = 2048  # measured at 148 scenes: the cell list also wins for SA2 (2048 points, r = 0.4, nsample = 32)
 GRAPH_CACHE_SIZE = 6     # CUDA graphs kept per engine (LRU): each pins the buffers of one input-shape signature
 GRAPH_TOKEN_BUCKET = 16  # text length is padded to a multiple of this before a graph is looked up
 GRID_RULE_K = 200.0  # cell list when nsample >= K * radius^2 (metres): r=.2 -> 8, r=.4 -> 32, r=.8 -> 128
@@ -61,7 +61,7 @@ def grid_ball_query_rule(n, radius, nsample, m):
     `pointnet2._ext` drop-in.  The scan stops at the nsample-th hit, so it wins for big balls /
     small groups; the cell list tests ~27 cells per centre whatever the cloud size.  Measured on
     50k-point scenes (profiles/, configs[4]): the cell list wins for r = 0.2 at every nsample."""
-    return n >= GRID_BALL_QUERY_MIN_POINTS and nsample <= 64 and nsample >= GRID_RULE_K * radius * radius
+    return n >= GRID_BALL_QUERY_MIN_POINTS and nsample <= 64 and nsample >= GRID_RULE_K * radius * radius - 1e-6
 
 
 # ------------------------------------------------------------------------------ weight packing
@@ -85,6 +85,7 @@ def _plain(sd, name):
     return (W.reshape(W.shape[0], -1).float().contiguous(), None if b is None else b.float().contiguous())
 
 
+FPS_GRID_MIN_POINTS = 8192  # ... and points per scene
 FPS_GRID_MIN_BATCH = 38  # scenes from which SA1's FPS runs as the bucketed one-CTA-per-scene kernel over the cell list
 # (bd_fps_grid: a single wave up to 148 scenes, 3.4 - 3.95 ms whatever the batch) instead of the register-resident
 # cluster kernel (37 scenes per wave of 2.18 ms: 4.36 ms at 64 scenes, 8.72 ms at 128)
@@ -663,7 +664,7 @@ class ForwardEngine:
         feats, ld_feats, C = pc[..., 3:], ld, C_in
         self._grid = None
         lib = _lib.load()
-        if GRID_BALL_QUERY_MIN_POINTS <= N <= lib.bd_fps_grid_capacity() and B >= FPS_GRID_MIN_BATCH:
+        if FPS_GRID_MIN_POINTS <= N <= lib.bd_fps_grid_capacity() and B >= FPS_GRID_MIN_BATCH:
             # the cell list of SA1's ball query is built first: its cell order also drives the
             # bucketed furthest-point sampling (bd_fps_grid)
             ws = self._empty(lib.bd_ball_query_grid_workspace_bytes(B, N), dtype=torch.uint8)

@@ -34,3 +34,25 @@ i2 = torch.zeros(1, 256, dtype=torch.int32, device="cuda")
 _lib.call("bd_fps", big.data_ptr(), 3, 1, 50000, 256, None, i2.data_ptr())  # 16-CTA cluster kernel (DSMEM st.async)
 torch.cuda.synchronize()
 print("sanitize target finished:", precision, "graph" if graph else "eager", int(idx.sum()), int(out.sum()), int(i2.sum()))
+# round-2b additions: the text side (RoBERTa engine incl. the head_dim-64 direct attention) and the device matcher
+if "--no-extras" not in sys.argv:
+    from transformers import RobertaConfig, RobertaModel
+    from butd_detr_b200 import text_encoder
+    from butd_detr_b200.matcher import HungarianMatcher
+    torch.manual_seed(0)
+    cfg = RobertaConfig(vocab_size=1000, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1,
+                        num_hidden_layers=2)
+    eng = text_encoder.from_module(RobertaModel(cfg).cuda(), precision)
+    ids = torch.randint(3, 1000, (3, 21)).cuda()
+    mask = torch.ones(3, 21, dtype=torch.long).cuda()
+    mask[1, 15:] = 0
+    ids[1, 15:] = 1
+    hid = eng.forward(ids, mask)
+    g = torch.Generator().manual_seed(1)
+    outs = {"pred_logits": torch.randn(2, 32, 256, generator=g).cuda(),
+            "pred_boxes": torch.cat([torch.rand(2, 32, 3, generator=g), torch.rand(2, 32, 3, generator=g) + 0.1], -1).cuda()}
+    tg = [{"boxes": torch.cat([torch.rand(n, 3, generator=g), torch.rand(n, 3, generator=g) + 0.1], -1).cuda(),
+           "positive_map": torch.rand(n, 256, generator=g).cuda(), "labels": torch.zeros(n, dtype=torch.int64).cuda()} for n in (5, 32)]
+    pairs = HungarianMatcher(1, 0, 2, True)(outs, tg)
+    torch.cuda.synchronize()
+    print("extras finished:", bool(torch.isfinite(hid).all()), [int(p[0].sum()) for p in pairs])
