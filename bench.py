@@ -622,9 +622,11 @@ def attention_summary(scenes_per_s_per_gpu, rooflines):
         t = sum(r["mean_launch_ms"] * r["launches"] for r in att)
         out["attention_kernel_tflops"] = fl / (t * 1e-3) / 1e12
         out["attention_kernel_flop_frac"] = out["attention_kernel_tflops"] / peak
-    p = os.path.join(ROOT, "profiles", "r02_attention_pipe.json")
-    if os.path.exists(p):
-        out["tensor_pipe_pct_ncu"] = json.load(open(p))
+    for f in ("r02b_attention_pipe.json", "r02_attention_pipe.json"):
+        p = os.path.join(ROOT, "profiles", f)
+        if os.path.exists(p):
+            out["tensor_pipe_pct_ncu"] = json.load(open(p))
+            break
     return out
 
 
@@ -647,10 +649,20 @@ def algorithmic_work(name, a):
         return "hbm", a[3] * (12 * a[4] + 12 * a[5] + 4 * a[5] * a[7])
     if name == "bd_attention_tc":  # ..., B, H, Lq, Lk, hd at 13..17 : QK^T + PV
         return "tensor", 4.0 * a[13] * a[14] * a[15] * a[16] * a[17]
+    if name == "bd_attention_tc_h":  # io_half at 13, then B, H, Lq, Lk, hd at 14..18
+        return "tensor", 4.0 * a[14] * a[15] * a[16] * a[17] * a[18]
+    if name == "bd_attention_tc_packed":  # Q, ldq, sq_b, mask, O, ldo, so_b, io_half, B, H, Lq, Lk, hd at 8..12
+        return "tensor", 4.0 * a[8] * a[9] * a[10] * a[11] * a[12]
     if name == "bd_linear_tc":  # M, N, K at 8..10
         return "tensor", 2.0 * a[8] * a[9] * a[10]
+    if name == "bd_linear_tc_h":  # x, lda, a_half, add, lda2, Wp, b, out, ldy, y_half, then M, N, K at 10..12
+        return "tensor", 2.0 * a[10] * a[11] * a[12]
     if name == "bd_linear_ln_tc":  # M, N, K at 13..15
         return "tensor", 2.0 * a[13] * a[14] * a[15]
+    if name == "bd_linear_ln_tc_h":  # ..., out, ldy, shadow, ld_shadow, then M, N, K at 14..16
+        return "tensor", 2.0 * a[14] * a[15] * a[16]
+    if name == "bd_sa_mlp_tc_h":  # C at 3, B, n, m, ns at 8..11, N0 / N1 / N2 at 15 / 18 / 21
+        return "tensor", 2.0 * a[8] * a[10] * a[11] * ((a[3] + 3) * a[15] + a[15] * a[18] + a[18] * a[21])
     if name == "bd_linear_pool_tc":  # M, N, K at 6..8
         return "tensor", 2.0 * a[6] * a[7] * a[8]
     if name == "bd_sa_group_linear_tc":  # C at 3, B, n, m, ns at 7..10, N at 16
@@ -669,22 +681,26 @@ def measured_traffic(name, B):
     committed `ncu --set full` capture (profiles/r02_traffic.json).  The capture was taken at the batch size
     named there; for another batch size the per-scene traffic is scaled to this run's batch (every kernel of
     the path works scene by scene) — `roofline.traffic_captured_at_batch` says which."""
-    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
-    if not os.path.exists(p):
-        p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(p):
-        return None
-    e = json.load(open(p)).get(name)
+    e = _traffic_entry(name)
     if not e:
         return None
     return int(e["dram_bytes_per_launch"] * B / e["batch"])
 
 
+def _traffic_entry(name):
+    """Entry of the newest committed traffic table for a C-ABI entry point (the `_h` entry points are the 16-bit
+    variants of the same kernels)."""
+    for f in ("r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", f)
+        if os.path.exists(p):
+            t = json.load(open(p))
+            base = name[:-2] if name.endswith("_h") else name
+            return t.get(name) or t.get(base)
+    return None
+
+
 def traffic_batch(name):
-    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
-    if not os.path.exists(p):
-        return None
-    e = json.load(open(p)).get(name)
+    e = _traffic_entry(name)
     return e["batch"] if e else None
 
 
