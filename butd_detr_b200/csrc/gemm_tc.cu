@@ -729,6 +729,9 @@ extern "C" int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda
 // 16-bit activation variants (fp16 operand mode only, split = 1, no A2).  a_half: A is an fp16 (M, K) matrix
 // (lda in halfs, lda % 8 == 0); y_half: Y is written as fp16 rows (ldy in halfs, ldy % 8 == 0).  Values are the
 // ones the fp32 entry points produce followed by the fp16 rounding their consumers apply anyway.
+int bd_linear_stream_try(const void *A, int lda, const void *Wp, const float *bias, void *Y, int ldy, int M, int N, int K,
+                         int n_chunks, int BN, int n_sub, int relu, cudaStream_t stream);  // gemm_stream.cu
+
 extern "C" int bd_linear_tc_h(const void *A, int lda, int a_half, const float *A2, int lda2, const void *Wp,
                               const float *bias, void *Y, int ldy, int y_half, int M, int N, int K, int kc, int n_chunks,
                               int BN, int n_sub, int relu, bd_stream_t stream) {
@@ -740,6 +743,14 @@ extern "C" int bd_linear_tc_h(const void *A, int lda, int a_half, const float *A
   BD_REQUIRE(lda % (a_half ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, "bd_linear_tc_h: A rows must be 16-byte aligned");
   BD_REQUIRE(!y_half || (ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0), "bd_linear_tc_h: fp16 Y rows must be 16-byte aligned");
   BD_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && n_sub >= 1 && n_sub * BN <= 512, "bd_linear_tc_h: bad tiling");
+  if (a_half && y_half && !A2) {  // 16-bit rows in and out, more than one wave of tiles: the persistent kernel (gemm_stream.cu)
+    const int rs = bd_linear_stream_try(A, lda, Wp, bias, Y, ldy, M, N, K, n_chunks, BN, n_sub, relu, bd::as_stream(stream));
+    if (rs < 0) return -rs;
+    if (rs == 1) {
+      BD_CHECK_LAUNCH("bd_linear_tc_h");
+      return BD_OK;
+    }
+  }
   LinearTcParams p = {};
   p.A = static_cast<const float *>(A), p.A2 = A2, p.lda2 = lda2, p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp);
   p.Y = static_cast<float *>(Y), p.Y16 = static_cast<__half *>(Y), p.lda = lda, p.ldy = ldy, p.ldy16 = ldy;

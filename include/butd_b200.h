@@ -339,6 +339,11 @@ int bd_matcher_cost(const float *logits, const float *boxes, const float *tgt_bo
 int bd_hungarian(const float *cost, const int *tgt_offset, int B, int Q, int max_targets,
                  long long *match_q, long long *match_t, int *status, bd_stream_t stream);
 
+/* bd_linear_tc_h with fp16 rows in AND out, no second operand and more row tiles than SMs runs as a PERSISTENT
+ * kernel (csrc/gemm_stream.cu: operand copies of tile i + 1 under the MMAs, the TMEM drain and the store of tile
+ * i; bit-identical results).  on = 0 switches it off (A/B reference).  Default on. */
+int bd_linear_stream_set(int on);
+
 /* RoBERTa input embeddings (text side, reference call site models/bdetr.py:168 -> transformers
  * RobertaEmbeddings.forward): Y (B*L, D) = LayerNorm(word[ids] + position[pid] + token_type[0]) with
  * pid = pad_idx + running count of non-pad tokens (pad tokens: pad_idx).  ids (B,L) int64; word (vocab,D),

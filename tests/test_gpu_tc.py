@@ -406,3 +406,34 @@ def test_attention_tc_half_tensors(cuda_lib, B, Lq, Lk, masked, io, direct):
         s = s.masked_fill(mask[:, None, None, :], float("-inf"))
     want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
     torch.testing.assert_close(out.float(), want, rtol=6e-3, atol=6e-3)
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(151552 // 4, 288, 288, 0), (40000, 576, 288, 1), (33333, 256, 288, 1), (148 * 256, 864, 288, 1),
+                                        (20000, 288, 256, 0), (19000, 64, 288, 1)])
+def test_persistent_linear_equals_the_one_tile_kernel(cuda_lib, M, N, K, relu):
+    """fp16 rows in and out with more row tiles than SMs: the persistent kernel (gemm_stream.cu) must give the bits
+    of the one-tile-per-CTA kernel (same operand formats, MMA order and epilogue), ragged last tile included."""
+    from butd_detr_b200.engine import lin_tiling, pack_weight_tc
+    lib = cuda_lib.load()
+    g = _g(M + N)
+    A = (torch.randn(M, K, device="cuda", generator=g)).half()
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    wide, bn = lin_tiling(M, N)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 1, wide=wide, bn=bn)
+    outs = []
+    for on in (0, 1):
+        lib.bd_linear_stream_set(on)
+        try:
+            Y = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+            cuda_lib.call("bd_linear_tc_h", A.data_ptr(), K, 1, None, 0, Wp.data_ptr(), b.data_ptr(), Y.data_ptr(), N, 1, M, N, K,
+                          KC, nch, BN, nsub, relu)
+            torch.cuda.synchronize()
+        finally:
+            lib.bd_linear_stream_set(1)
+        outs.append(Y)
+    assert torch.equal(outs[0], outs[1])
+    want = F.linear(A.double(), W.half().double(), b.double())
+    if relu:
+        want = want.relu()
+    torch.testing.assert_close(outs[1].double(), want, rtol=2e-3, atol=2e-3)
