@@ -732,6 +732,10 @@ extern "C" int bd_linear_ln_tc(const float *A, int lda, const float *A2, int lda
 int bd_linear_stream_try(const void *A, int lda, const void *Wp, const float *bias, void *Y, int ldy, int M, int N, int K,
                          int n_chunks, int BN, int n_sub, int relu, cudaStream_t stream);  // gemm_stream.cu
 
+int bd_linear_ln_stream_try(const void *A, int lda, const void *Wp, const float *bias, const float *R, int ldr,
+                            const float *gamma, const float *beta, float eps, float *Y, int ldy, void *Y16, int ldy16, int M,
+                            int N, int K, int n_chunks, int BN, int n_sub, cudaStream_t stream);  // gemm_stream.cu
+
 extern "C" int bd_linear_tc_h(const void *A, int lda, int a_half, const float *A2, int lda2, const void *Wp,
                               const float *bias, void *Y, int ldy, int y_half, int M, int N, int K, int kc, int n_chunks,
                               int BN, int n_sub, int relu, bd_stream_t stream) {
@@ -778,6 +782,15 @@ extern "C" int bd_linear_ln_tc_h(const void *A, int lda, int a_half, const void 
                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
              "bd_linear_ln_tc_h: N, ldr, ldy must be multiples of 4 and R, Y, gamma, beta 16-byte aligned");
   BD_REQUIRE(!Y16 || (ldy16 % 4 == 0 && ldy16 >= N && (reinterpret_cast<uintptr_t>(Y16) & 7) == 0), "bd_linear_ln_tc_h: bad Y16");
+  if (a_half) {  // fp16 rows in, more row tiles than SMs: the persistent kernel (gemm_stream.cu)
+    const int rs = bd_linear_ln_stream_try(A, lda, Wp, bias, R, ldr, gamma, beta, eps, Y, ldy, Y16, ldy16, M, N, K, n_chunks, BN,
+                                           n_sub, bd::as_stream(stream));
+    if (rs < 0) return -rs;
+    if (rs == 1) {
+      BD_CHECK_LAUNCH("bd_linear_ln_tc_h");
+      return BD_OK;
+    }
+  }
   LinearTcParams p = {};
   p.A = static_cast<const float *>(A), p.bias = bias, p.Wp = static_cast<const __nv_bfloat16 *>(Wp), p.Y = Y;
   p.R = R, p.gamma = gamma, p.beta = beta, p.eps = eps, p.ldr = ldr;

@@ -437,3 +437,36 @@ def test_persistent_linear_equals_the_one_tile_kernel(cuda_lib, M, N, K, relu):
     if relu:
         want = want.relu()
     torch.testing.assert_close(outs[1].double(), want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,shadow", [(151552 // 4, 288, 288, True), (148 * 256 + 77, 288, 256, True), (20000, 288, 288, False),
+                                          (30001, 256, 320, True)])
+def test_persistent_linear_layernorm_equals_the_one_tile_kernel(cuda_lib, M, N, K, shadow):
+    """LayerNorm(R + A16 W^T + b) with more row tiles than SMs: the persistent kernel (two 64-row halves per tile)
+    must give the bits of linear_tc_kernel<1, 0>, fp16 copy included, ragged last tile included."""
+    from butd_detr_b200.engine import pack_weight_tc
+    lib = cuda_lib.load()
+    g = _g(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    R = torch.randn(M, N, device="cuda", generator=g)
+    gam, bet = torch.rand(N, device="cuda", generator=g) + 0.5, torch.randn(N, device="cuda", generator=g) * 0.1
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 1, full_rows=True)
+    outs = []
+    for on in (0, 1):
+        lib.bd_linear_stream_set(on)
+        try:
+            Y = torch.full((M, N), float("nan"), device="cuda")
+            Y16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16) if shadow else None
+            cuda_lib.call("bd_linear_ln_tc_h", A.data_ptr(), K, 1, Wp.data_ptr(), b.data_ptr(), R.data_ptr(), N, gam.data_ptr(),
+                          bet.data_ptr(), 1e-5, Y.data_ptr(), N, cuda_lib.ptr(Y16), N, M, N, K, KC, nch, BN, nsub)
+            torch.cuda.synchronize()
+        finally:
+            lib.bd_linear_stream_set(1)
+        outs.append((Y, Y16))
+    assert torch.equal(outs[0][0], outs[1][0])
+    if shadow:
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[1][1], outs[1][0].half())
+    want = F.layer_norm(R.double() + F.linear(A.double(), W.half().double(), b.double()), (N,), gam.double(), bet.double(), 1e-5).float()
+    torch.testing.assert_close(outs[1][0], want, rtol=2e-4, atol=2e-4)
