@@ -54,5 +54,22 @@ if "--no-extras" not in sys.argv:
     tg = [{"boxes": torch.cat([torch.rand(n, 3, generator=g), torch.rand(n, 3, generator=g) + 0.1], -1).cuda(),
            "positive_map": torch.rand(n, 256, generator=g).cuda(), "labels": torch.zeros(n, dtype=torch.int64).cuda()} for n in (5, 32)]
     pairs = HungarianMatcher(1, 0, 2, True)(outs, tg)
+    # the persistent linear kernels only run with more row tiles than SMs: 157 tiles here
+    import math
+    from butd_detr_b200.engine import lin_tiling, pack_weight_tc
+    M, N, K = 20000, 288, 288
+    A = torch.randn(M, K, device="cuda").half()
+    W = torch.randn(N, K, device="cuda") / math.sqrt(K)
+    bias = torch.randn(N, device="cuda")
+    wide, bn = lin_tiling(M, N)
+    Wp, (BN, KC, nch, nsub) = pack_weight_tc(W, 1, wide=wide, bn=bn)
+    Y16 = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    _lib.call("bd_linear_tc_h", A.data_ptr(), K, 1, None, 0, Wp.data_ptr(), bias.data_ptr(), Y16.data_ptr(), N, 1, M, N, K, KC, nch, BN,
+              nsub, 1)
+    Wr, (BN, KC, nch, nsub) = pack_weight_tc(W, 1, full_rows=True)
+    R, Y = torch.randn(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    gam, bet = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+    _lib.call("bd_linear_ln_tc_h", A.data_ptr(), K, 1, Wr.data_ptr(), bias.data_ptr(), R.data_ptr(), N, gam.data_ptr(), bet.data_ptr(),
+              1e-5, Y.data_ptr(), N, Y16.data_ptr(), N, M, N, K, KC, nch, BN, nsub)
     torch.cuda.synchronize()
-    print("extras finished:", bool(torch.isfinite(hid).all()), [int(p[0].sum()) for p in pairs])
+    print("extras finished:", bool(torch.isfinite(hid).all()), [int(p[0].sum()) for p in pairs], bool(torch.isfinite(Y).all()))
