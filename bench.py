@@ -622,7 +622,7 @@ def attention_summary(scenes_per_s_per_gpu, rooflines):
         t = sum(r["mean_launch_ms"] * r["launches"] for r in att)
         out["attention_kernel_tflops"] = fl / (t * 1e-3) / 1e12
         out["attention_kernel_flop_frac"] = out["attention_kernel_tflops"] / peak
-    for f in ("r02b_attention_pipe.json", "r02_attention_pipe.json"):
+    for f in ("r02c_attention_pipe.json", "r02b_attention_pipe.json", "r02_attention_pipe.json"):
         p = os.path.join(ROOT, "profiles", f)
         if os.path.exists(p):
             out["tensor_pipe_pct_ncu"] = json.load(open(p))
@@ -690,7 +690,7 @@ def measured_traffic(name, B):
 def _traffic_entry(name):
     """Entry of the newest committed traffic table for a C-ABI entry point (the `_h` entry points are the 16-bit
     variants of the same kernels)."""
-    for f in ("r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+    for f in ("r02c_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         p = os.path.join(ROOT, "profiles", f)
         if os.path.exists(p):
             t = json.load(open(p))
