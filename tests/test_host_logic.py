@@ -66,3 +66,27 @@ def test_bench_work_figures():
     assert not hasattr(bench, "PARITY_MEASURED")  # the error is measured in every run (bench.measure_parity)
     att = bench.attention_summary(4000.0, [])
     assert abs(att["attention_gemm_flop_roofline_frac"] - 4000 * 17.9e9 / (bench.tensor_peak() * 1e12)) < 1e-12
+
+
+def test_round_2b_modules_refuse_cpu_tensors():
+    """The text-side engine and the device matcher have no CPU path: they fail loudly on CPU inputs / devices."""
+    import pytest
+    import torch
+    from butd_detr_b200 import text_encoder
+    from butd_detr_b200.matcher import HungarianMatcher
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        text_encoder.RobertaEngine({}, None, "cpu")
+    out = {"pred_logits": torch.zeros(1, 4, 8), "pred_boxes": torch.zeros(1, 4, 6)}
+    tg = [{"boxes": torch.zeros(2, 6), "positive_map": torch.zeros(2, 8), "labels": torch.zeros(2, dtype=torch.int64)}]
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        HungarianMatcher(1, 5, 2, True)(out, tg)
+
+
+def test_grid_ball_query_rule_values():
+    """One rule for the engine and the pointnet2._ext drop-in: the cell list for SA1 (50k points, r = 0.2) and SA2
+    (2048 points, r = 0.4, nsample = 32 — exactly on the nsample >= 200 r^2 boundary), the ordered scan elsewhere."""
+    from butd_detr_b200.engine import grid_ball_query_rule
+    assert grid_ball_query_rule(50000, 0.2, 64, 2048) and grid_ball_query_rule(50000, 0.2, 16, 2048)
+    assert grid_ball_query_rule(2048, 0.4, 32, 1024)
+    assert not grid_ball_query_rule(1024, 0.8, 16, 512) and not grid_ball_query_rule(512, 1.2, 16, 256)
+    assert not grid_ball_query_rule(50000, 0.8, 16, 2048) and not grid_ball_query_rule(50000, 0.2, 100, 2048)
