@@ -31,6 +31,7 @@ _SIGNATURES = {
     "bd_linear_stream_set": [_I],
     "bd_matcher_cost": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P],
     "bd_hungarian": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "bd_linear_smallk": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bd_roberta_embed": [_P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "bd_attention_tc_pack_kv": [_P, _I, _LL, _P, _I, _LL, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bd_attention_tc_packed": [_P, _I, _LL, _P, _P, _I, _LL, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P],

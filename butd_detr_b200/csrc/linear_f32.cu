@@ -6,6 +6,8 @@
 //
 // Both operands are K-major (activations are token-major rows, W is torch's (N,K) layout), so
 // global loads are float4 along K and the tile is transposed into shared memory once.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -144,6 +146,55 @@ linear_f32_kernel(const float *__restrict__ A, int lda, const float *__restrict_
   }
 }
 
+
+// Narrow-input layers (K <= 8: the first layer of the learned position embeddings — xyz, or centre + size, or a
+// detected box — models/modules.py PositionEmbeddingLearned, models/bdetr.py:217-225): 3 to 8 multiply-adds per
+// output, i.e. a pure write stream.  W^T and the bias sit in shared memory, one warp walks over rows, a lane
+// owns column pairs (4- or 8-byte stores, a full line per warp); the row can be written as fp16 (HALF: the operand
+// format of the layer that follows, same fp32 value rounded once).  Same operation order as linear_f32_kernel
+// (fma over ascending k, bias added last).
+template <bool HALF>
+__global__ void __launch_bounds__(256)
+linear_smallk_kernel(const float *__restrict__ A, int lda, const float *__restrict__ W, const float *__restrict__ bias,
+                     void *__restrict__ Y, int ldy, int M, int N, int K, int relu) {
+  extern __shared__ float sk_smem[];  // Wt[K][Np] then bias[Np], Np = N rounded up to 2
+  const int Np = (N + 1) & ~1;
+  float *Wt = sk_smem, *bs = sk_smem + K * Np;
+  for (int i = threadIdx.x; i < K * Np; i += blockDim.x) {
+    const int k = i / Np, n = i - k * Np;
+    Wt[i] = n < N ? __ldg(W + static_cast<long long>(n) * K + k) : 0.f;
+  }
+  for (int i = threadIdx.x; i < Np; i += blockDim.x) bs[i] = (bias && i < N) ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long r = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < M; r += static_cast<long long>(gridDim.x) * wpb) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = k < K ? __ldg(A + r * lda + k) : 0.f;
+    for (int n = 2 * lane; n < N; n += 64) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < K) {
+          const float2 w = *reinterpret_cast<const float2 *>(Wt + k * Np + n);
+          a0 = fmaf(x[k], w.x, a0), a1 = fmaf(x[k], w.y, a1);
+        }
+      }
+      a0 += bs[n], a1 += bs[n + 1];
+      if (relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
+      if (HALF) {
+        __half *y = static_cast<__half *>(Y) + r * ldy + n;
+        if (n + 1 < N) *reinterpret_cast<__half2 *>(y) = __floats2half2_rn(fminf(fmaxf(a0, -65504.f), 65504.f), fminf(fmaxf(a1, -65504.f), 65504.f));
+        else y[0] = __float2half_rn(fminf(fmaxf(a0, -65504.f), 65504.f));
+      } else {
+        float *y = static_cast<float *>(Y) + r * ldy + n;
+        if (n + 1 < N) *reinterpret_cast<float2 *>(y) = make_float2(a0, a1);
+        else y[0] = a0;
+      }
+    }
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 void launch(const float *A, int lda, const float *A2, int lda2, const float *W, const float *bias, float *Y, int ldy,
             int M, int N, int K, int relu, cudaStream_t s) {
@@ -175,5 +226,24 @@ extern "C" int bd_linear_f32(const float *A, int lda, const float *A2, int lda2,
   else
     launch<32, 64, 2, 4>(A, lda, A2, lda2, W, bias, Y, ldy, M, N, K, relu, s);
   BD_CHECK_LAUNCH("bd_linear_f32");
+  return BD_OK;
+}
+
+// Y (M, N) = act(A (M, K <= 8) . W^T + bias), fp32 rows or (y_half) fp16 rows; ldy % 2 == 0 and Y 8-byte aligned
+// (fp32) / 4-byte aligned (fp16).  relu = 0 / 1.
+extern "C" int bd_linear_smallk(const float *A, int lda, const float *W, const float *bias, void *Y, int ldy, int y_half,
+                                int M, int N, int K, int relu, bd_stream_t stream) {
+  BD_REQUIRE(A && W && Y, "bd_linear_smallk: null pointer");
+  BD_REQUIRE(M > 0 && N > 0 && K > 0 && K <= 8 && lda >= K && ldy >= N && ldy % 2 == 0 && (relu == 0 || relu == 1) &&
+                 (reinterpret_cast<uintptr_t>(Y) & 7) == 0 && N <= 4096,
+             "bd_linear_smallk: needs 0 < K <= 8, N <= 4096, even ldy, 8-byte aligned Y, relu in {0, 1}");
+  const int Np = (N + 1) & ~1;
+  const size_t smem = sizeof(float) * static_cast<size_t>(K + 1) * Np;
+  const int blocks = bd::ceil_div(M, 8 * 16) < 4 * bd::sm_count() ? bd::ceil_div(M, 8 * 16) : 4 * bd::sm_count();
+  if (y_half)
+    linear_smallk_kernel<true><<<blocks > 0 ? blocks : 1, 256, smem, bd::as_stream(stream)>>>(A, lda, W, bias, Y, ldy, M, N, K, relu);
+  else
+    linear_smallk_kernel<false><<<blocks > 0 ? blocks : 1, 256, smem, bd::as_stream(stream)>>>(A, lda, W, bias, Y, ldy, M, N, K, relu);
+  BD_CHECK_LAUNCH("bd_linear_smallk");
   return BD_OK;
 }

@@ -327,6 +327,14 @@ class ForwardEngine:
                       out.stride(0), int(y_half), M, N, K, KC, n_chunks, BN, n_sub, int(relu))
             return out
         assert not a_half, key
+        if K <= 8 and add is None and N % 2 == 0 and (out is None or (out.stride(0) % 2 == 0 and out.data_ptr() % 8 == 0)):
+            # narrow-input layer (position embeddings): a write stream; fp16 rows when the next layer reads them
+            y_half = bool(half_out and self.half and out is None)
+            if out is None:
+                out = self._empty(M, N, dtype=torch.float16 if y_half else torch.float32)
+            _lib.call("bd_linear_smallk", x.data_ptr(), x.stride(0), W.data_ptr(), _lib.ptr(b), out.data_ptr(), out.stride(0),
+                      int(y_half), M, N, K, int(bool(relu)))
+            return out
         if out is None:
             out = self._empty(M, N)
         assert out.stride(1) == 1
@@ -491,7 +499,7 @@ class ForwardEngine:
         return self.lin_ln(self.lin(x, key + ".0", relu=True, half_out=True), key + ".1", x, ln_key)
 
     def posembed(self, x, key):
-        return self.lin(self.lin(x, key + ".0", relu=True), key + ".1")
+        return self.lin(self.lin(x, key + ".0", relu=True, half_out=True), key + ".1")
 
     def head(self, feats, base_xyz, key, out):
         """ClsAgnosticPredictHead.forward (models/modules.py:135-180) on token-major rows (n, E).
@@ -816,7 +824,7 @@ class ForwardEngine:
                 D = boxes.shape[1]
                 dmask_u8 = (~inputs["det_bbox_label_mask"]).to(torch.uint8).contiguous()
                 det = self._empty(B * D, E)
-                h = self.lin(boxes.view(B * D, 6), "box_embeddings.0", relu=True)
+                h = self.lin(boxes.view(B * D, 6), "box_embeddings.0", relu=True, half_out=True)
                 self.lin(h, "box_embeddings.1", out=det[:, :128])
                 table = self.W["butd_class_embeddings"][0]
                 emb = self._empty(B * D, table.shape[1])

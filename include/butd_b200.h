@@ -344,6 +344,13 @@ int bd_hungarian(const float *cost, const int *tgt_offset, int B, int Q, int max
  * i; bit-identical results).  on = 0 switches it off (A/B reference).  Default on. */
 int bd_linear_stream_set(int on);
 
+/* Narrow-input layers, K <= 8 (the first layer of the learned position embeddings: models/modules.py
+ * PositionEmbeddingLearned on xyz / centre + size / detected boxes): Y (M,N) = act(A (M,K) W^T + bias), W (N,K) in
+ * torch's layout, fp32 rows or (y_half != 0) fp16 rows — the operand of the layer that follows; ldy even, Y 8-byte
+ * aligned, relu 0 / 1.  Same operation order as bd_linear_f32. */
+int bd_linear_smallk(const float *A, int lda, const float *W, const float *bias, void *Y, int ldy,
+                     int y_half, int M, int N, int K, int relu, bd_stream_t stream);
+
 /* RoBERTa input embeddings (text side, reference call site models/bdetr.py:168 -> transformers
  * RobertaEmbeddings.forward): Y (B*L, D) = LayerNorm(word[ids] + position[pid] + token_type[0]) with
  * pid = pad_idx + running count of non-pad tokens (pad tokens: pad_idx).  ids (B,L) int64; word (vocab,D),

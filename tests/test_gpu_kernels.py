@@ -198,3 +198,25 @@ def test_fp_interp_concat_rows_kernel_equals_the_element_kernel(cuda_lib, oracle
     cuda_lib.call("bd_fp_interp_concat_h", d2_d.data_ptr(), i3_d.data_ptr(), kf_d.data_ptr(), C2, uf_d.data_ptr(), C1, B, n, m,
                   x16.data_ptr(), 1)
     assert torch.equal(x16, x.half())
+
+
+@pytest.mark.parametrize("M,N,K,relu,half", [(5000, 288, 3, 1, 1), (777, 288, 6, 1, 0), (129, 128, 6, 0, 1), (64, 30, 8, 1, 0)])
+def test_linear_smallk(cuda_lib, M, N, K, relu, half):
+    """Narrow-input layer (first layer of the position embeddings): fp32 rows equal bd_linear_f32's (same operation
+    order), fp16 rows are those values rounded once."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    ref = torch.full((M, N), float("nan"), device="cuda")
+    cuda_lib.call("bd_linear_f32", A.data_ptr(), K, None, 0, W.data_ptr(), b.data_ptr(), ref.data_ptr(), N, M, N, K, relu)
+    Y = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16 if half else torch.float32)
+    cuda_lib.call("bd_linear_smallk", A.data_ptr(), K, W.data_ptr(), b.data_ptr(), Y.data_ptr(), N, half, M, N, K, relu)
+    want = F.linear(A.double(), W.double(), b.double())
+    if relu:
+        want = want.relu()
+    torch.testing.assert_close(ref.double(), want, rtol=1e-5, atol=1e-5)
+    if half:
+        assert torch.equal(Y, ref.half())
+    else:
+        assert torch.equal(Y, ref)
