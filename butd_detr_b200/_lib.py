@@ -28,6 +28,7 @@ _SIGNATURES = {
     "bd_fps_grid_stats": [_I, _P],
     "bd_attention_tc_set_small_nk": [_I],
     "bd_attention_tc_set_direct": [_I],
+    "bd_attention_tc_set_short": [_I],
     "bd_linear_stream_set": [_I],
     "bd_matcher_cost": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P],
     "bd_hungarian": [_P, _P, _I, _I, _I, _P, _P, _P, _P],

@@ -783,6 +783,199 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
   if (warp == 0) tc::tmem_dealloc(tmem, TM_COLS);
 }
 
+
+// ------------------------------------------------------------------ short key sequences (Lk <= 128)
+// One key tile: no online softmax, no running accumulators — and no reason to spend 256 TMEM columns and 160
+// registers per thread on a CTA.  The launches with 80 text tokens as keys (1024 x 80, 256 x 80, 80 x 80) do almost
+// no arithmetic and are bound by the fixed latency chain of a CTA (copies -> S -> softmax -> P.V -> write-out) at two
+// CTAs per SM.  This variant keeps P in SHARED memory (over the Q and K tiles, dead once S is complete) so that O can
+// be accumulated over the score columns: 128 TMEM columns, 53 KB of shared memory and <= 85 registers per thread,
+// i.e. FOUR CTAs per SM.  fp16 K / V rows by tensor copy as in the DIRECT variant (same column shift for odd
+// heads), same arithmetic: p = 2^(s - max), fp16 P, denominators from the ones tile.
+constexpr uint32_t SH_SMEM = 3 * QK_PART + 2 * ONES_BLK + 1024;  // Q | K | V | ones
+__global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char *sQ = smem, *sK = sQ + QK_PART, *sV = sK + QK_PART, *sOnes = sV + QK_PART;
+  unsigned char *sP = smem;  // two blocks of 64 keys x 128 rows x 128 B over Q | K
+  __shared__ __align__(8) unsigned long long bar_q, bar_kf, bar_vf, bar_s, bar_p, bar_o;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+  const int lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+  const int shift = (h & 1) * 4;
+  const int nch = (min(WS_BK, p.Lk) + 31) >> 5;  // 32-key chunks that hold keys
+
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 128);
+  if (tid == 32) {
+    tc::mbar_init(tc::smem_u32(&bar_q), 4);
+    tc::mbar_init(tc::smem_u32(&bar_kf), 1);
+    tc::mbar_init(tc::smem_u32(&bar_vf), 1);
+    tc::mbar_init(tc::smem_u32(&bar_s), 1);
+    tc::mbar_init(tc::smem_u32(&bar_p), 128);
+    tc::mbar_init(tc::smem_u32(&bar_o), 1);
+    tc::fence_mbar_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xFFFFFFFFu, tmem_base_s, 0);
+  bd::pdl_launch_dependents();
+  bd::pdl_wait();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_kf), QK_PART);
+      tc::tma_load_2d(tc::smem_u32(sK), &p.tmK, h * AT_HD - shift, b * p.Lk, tc::smem_u32(&bar_kf));
+      tc::mbar_arrive_expect_tx(tc::smem_u32(&bar_vf), QK_PART);
+      tc::tma_load_2d(tc::smem_u32(sV), &p.tmV, h * AT_HD - shift, b * p.Lk, tc::smem_u32(&bar_vf));
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc_s = tc::idesc_ab(1, AT_BM, 32 * nch), idesc_o = tc::idesc_ab(1, AT_BM, AT_NV) | tc::idesc_b_mn,
+                   idesc_1 = tc::idesc_ab(1, AT_BM, 16);
+    tc::mbar_wait(tc::smem_u32(&bar_q), 0);
+    tc::mbar_wait(tc::smem_u32(&bar_kf), 0);
+    tc::fence_after_sync();
+    if (tc::elect_one()) {
+#pragma unroll
+      for (int s = 0; s < AT_NV / 16; ++s)
+        tc::mma_bf16(tmem, tc::smem_desc_sw128(tc::smem_u32(sQ) + s * 32), tc::smem_desc_sw128(tc::smem_u32(sK) + s * 32), idesc_s,
+                     s > 0 ? 1u : 0u);
+      tc::mma_commit(tc::smem_u32(&bar_s));
+    }
+    __syncwarp();
+    tc::mbar_wait(tc::smem_u32(&bar_p), 0);
+    tc::mbar_wait(tc::smem_u32(&bar_vf), 0);
+    tc::fence_after_sync();
+    if (tc::elect_one()) {
+      for (int s = 0; s < 2 * nch; ++s) {  // 16 keys per step
+        const uint64_t dp = tc::smem_desc_sw128(tc::smem_u32(sP) + (s >> 2) * QK_PART + (s & 3) * 32);
+        tc::mma_bf16(tmem, dp, tc::smem_desc_sw128_mn(tc::smem_u32(sV) + s * 2048), idesc_o, s > 0 ? 1u : 0u);
+        tc::mma_bf16(tmem + AT_NV, dp, tc::smem_desc_sw128(tc::smem_u32(sOnes) + (s >> 2) * ONES_BLK + (s & 3) * 32), idesc_1,
+                     s > 0 ? 1u : 0u);
+      }
+      tc::mma_commit(tc::smem_u32(&bar_o));
+    }
+    __syncwarp();
+  } else {
+    // ---- Q rows -> operand tile (scale * log2 e folded in; zero outside the head's 36 dims), ones tile
+    {
+      const long long q_off = b * p.sq_b + h * AT_HD;
+      for (int e = tid - 64; e < AT_BM * 6; e += 128) {
+        const int rr = e / 6, ch = e - rr * 6;
+        const int q = qt * AT_BM + rr;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int d0 = ch * 8 - shift;
+        const bool first = d0 >= 0 && d0 < AT_HD, second = d0 + 4 < AT_HD;
+        if (q < p.Lq && (first || second)) {
+          load_chunk8(p.Q, q_off + static_cast<long long>(q) * p.ldq + d0, p.q16, second, v, first);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= p.scale_log2;
+        }
+        uint4 hi, lo;
+        tc::cvt8(1, v, hi, lo);
+        *reinterpret_cast<uint4 *>(sQ + tc::sw128_off(rr, ch)) = hi;
+      }
+      for (int e = tid - 64; e < 2 * static_cast<int>(ONES_BLK) / 16; e += 128) {
+        const uint32_t one2 = (e & 127) < 8 ? 0x3C003C00u : 0u;
+        *reinterpret_cast<uint4 *>(sOnes + e * 16) = make_uint4(one2, one2, one2, one2);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_q));
+    }
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tS = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const unsigned char *mask = p.mask ? p.mask + static_cast<long long>(b) * p.Lk : nullptr;
+    uint32_t vw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int key = c * 32 + lane;
+      vw[c] = __ballot_sync(0xFFFFFFFFu, key < p.Lk && !(mask && mask[key]));
+    }
+    tc::mbar_wait(tc::smem_u32(&bar_s), 0);
+    tc::fence_after_sync();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nch) {
+        uint32_t a[32];
+        tc::tmem_ld32(tS + c * 32, a);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if ((vw[c] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(a[i]));
+      }
+    }
+    const bool dead = mx == -INFINITY;  // every key masked
+    const float neg_m = dead ? 0.f : -mx;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nch) {
+        uint32_t a[32], o[16];
+        tc::tmem_ld32(tS + c * 32, a);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = tc::ex2_approx(__uint_as_float(a[i]) + neg_m), p1 = tc::ex2_approx(__uint_as_float(a[i + 1]) + neg_m);
+          if (dead || !((vw[c] >> i) & 1u)) p0 = 0.f;
+          if (dead || !((vw[c] >> (i + 1)) & 1u)) p1 = 0.f;
+          o[i >> 1] = tc::pack_f16x2(p0, p1);
+        }
+        unsigned char *blk = sP + (c >> 1) * QK_PART;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4 *>(blk + tc::sw128_off(row, (c & 1) * 4 + q4)) = make_uint4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+      }
+    }
+    tc::fence_before_sync();        // the scores have been read: O may overwrite their columns
+    tc::fence_proxy_async_smem();   // P is read by the tensor core (async proxy)
+    tc::mbar_arrive(tc::smem_u32(&bar_p));
+    tc::mbar_wait(tc::smem_u32(&bar_o), 0);
+    tc::fence_after_sync();
+    {
+      uint32_t a[32], c8[8], l;
+      tc::tmem_ld32(tS, a);
+      tc::tmem_ld8(tS + 32, c8);
+      tc::tmem_ld1(tS + AT_NV, l);
+      tc::tmem_ld_wait();
+      const int q = qt * AT_BM + row;
+      if (q < p.Lq) {
+        float o[40];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(a[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[32 + i] = __uint_as_float(c8[i]);
+        if (shift) {
+#pragma unroll
+          for (int d = 0; d < AT_HD; ++d) o[d] = o[d + 4];
+        }
+        const float l_run = __uint_as_float(l);
+        const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
+        const long long o_off = b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
+#pragma unroll
+        for (int d = 0; d < AT_HD; d += 4) {
+          float4 o4 = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+          if (l_run == 0.f) o4 = make_float4(NAN, NAN, NAN, NAN);
+          if (p.o16) {
+            __half2 h0 = __floats2half2_rn(o4.x, o4.y), h1 = __floats2half2_rn(o4.z, o4.w);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.O) + o_off + d) =
+                make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+          } else {
+            *reinterpret_cast<float4 *>(p.O + o_off + d) = o4;
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
 }  // namespace
 
 // Implementation switch (A/B measurements and the parity tests of both kernels): 1 = the
@@ -793,6 +986,11 @@ static int g_attn_impl = 1, g_attn_dbg = 0;
 // 80x1024 0.159 vs 0.187, 80x80 0.037 vs 0.046 — so the default is "always".  The bf16x3 mode keeps two ping-ponged
 // tiles per CTA: its operand tiles (hi + lo) leave room for one CTA per SM either way.
 static int g_attn_small_nk = 1 << 30;
+static int g_attn_short = 1;   // one key tile (Lk <= 128), fp16 K / V, head dim 36: the four-CTAs-per-SM kernel
+extern "C" int bd_attention_tc_set_short(int on) {
+  g_attn_short = on != 0;
+  return BD_OK;
+}
 static int g_attn_direct = 1;  // fp16 K / V: tensor copies from the projection output instead of the pack kernel
 extern "C" int bd_attention_tc_set_direct(int on) {
   g_attn_direct = on != 0;
@@ -919,6 +1117,7 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM2S);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_DIRECT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ws_kernel<1, 1, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_DIRECT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM);
     return e;
   }), "bd_attention_tc");
   cudaStream_t s = bd::as_stream(stream);
@@ -948,7 +1147,9 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
         BD_REQUIRE(r == CUDA_SUCCESS, "bd_attention_tc: cuTensorMapEncodeTiled failed (%d) for B=%d Lk=%d ld=%d",
                    static_cast<int>(r), B, Lk, which ? ldv : ldk);
       }
-      if (hd == 64)
+      if (hd == AT_HD && p.nk == 1 && g_attn_short)
+        BD_CUDA(bd::launch_pdl(attention_short_kernel, grid, dim3(WS_THREADS1), SH_SMEM, s, p), "bd_attention_tc");
+      else if (hd == 64)
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true, 64>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");
       else
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");

@@ -351,6 +351,11 @@ int bd_linear_stream_set(int on);
 int bd_linear_smallk(const float *A, int lda, const float *W, const float *bias, void *Y, int ldy,
                      int y_half, int M, int N, int K, int relu, bd_stream_t stream);
 
+/* Key sequences of at most 128 keys (one key tile) with fp16 K / V rows and head_dim 36 run a dedicated kernel: P
+ * in shared memory, O over the score columns — 128 TMEM columns, four CTAs per SM (these launches are bound by the
+ * per-CTA latency chain, not by arithmetic).  on = 0: the general kernel (A/B reference).  Default on. */
+int bd_attention_tc_set_short(int on);
+
 /* RoBERTa input embeddings (text side, reference call site models/bdetr.py:168 -> transformers
  * RobertaEmbeddings.forward): Y (B*L, D) = LayerNorm(word[ids] + position[pid] + token_type[0]) with
  * pid = pad_idx + running count of non-pad tokens (pad tokens: pad_idx).  ids (B,L) int64; word (vocab,D),

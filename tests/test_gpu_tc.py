@@ -470,3 +470,44 @@ def test_persistent_linear_layernorm_equals_the_one_tile_kernel(cuda_lib, M, N, 
         assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[1][1], outs[1][0].half())
     want = F.layer_norm(R.double() + F.linear(A.double(), W.half().double(), b.double()), (N,), gam.double(), bet.double(), 1e-5).float()
     torch.testing.assert_close(outs[1][0], want, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 80, True), (3, 256, 128, False), (2, 80, 80, True), (1, 300, 33, True),
+                                            (2, 130, 96, False), (1, 128, 1, False)])
+def test_attention_short_keys_kernel(cuda_lib, B, Lq, Lk, masked):
+    """Lk <= 128 with fp16 K / V: the four-CTAs-per-SM kernel (P in shared memory, O over the score columns) against
+    fp64 torch and against the general kernel (same arithmetic: equal up to the accumulation order of P.V)."""
+    H, hd = 8, 36
+    E = H * hd
+    lib = cuda_lib.load()
+    g = _g(Lq * 7 + Lk)
+    q32 = torch.randn(B, Lq, E, device="cuda", generator=g)
+    kv32 = torch.randn(B, Lk, 2 * E, device="cuda", generator=g)
+    q, kv = q32.half(), kv32.half()
+    k, v = kv[..., :E], kv[..., E:]
+    mask = None
+    if masked:
+        lens = torch.randint(1, Lk + 1, (B,), generator=torch.Generator().manual_seed(Lk))
+        lens[0] = Lk
+        mask = (torch.arange(Lk)[None] >= lens[:, None]).cuda()
+    m8 = mask.to(torch.uint8).contiguous() if masked else None
+    outs = []
+    for on in (1, 0):
+        lib.bd_attention_tc_set_short(on)
+        try:
+            out = torch.full((B, Lq, E), float("nan"), device="cuda", dtype=torch.float16)
+            cuda_lib.call("bd_attention_tc_h", q.data_ptr(), E, Lq * E, k.data_ptr(), 2 * E, Lk * 2 * E, v.data_ptr(), 2 * E,
+                          Lk * 2 * E, cuda_lib.ptr(m8), out.data_ptr(), E, Lq * E, 15, B, H, Lq, Lk, hd, 1.0 / math.sqrt(hd), 1, None)
+            torch.cuda.synchronize()
+        finally:
+            lib.bd_attention_tc_set_short(1)
+        outs.append(out)
+    qh = q.double().reshape(B, Lq, H, hd).transpose(1, 2)
+    kh = k.double().reshape(B, Lk, H, hd).transpose(1, 2)
+    vh = v.double().reshape(B, Lk, H, hd).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if masked:
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    want = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+    torch.testing.assert_close(outs[0].float(), want, rtol=6e-3, atol=6e-3)
+    torch.testing.assert_close(outs[0].float(), outs[1].float(), rtol=2e-3, atol=2e-3)

@@ -12,6 +12,8 @@ if sys.argv[1] != "-":
         if not hasattr(probe, k):
             del _lib._SIGNATURES[k]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+if os.environ.get("BD_SHORT_OFF"):
+    _lib.load().bd_attention_tc_set_short(0)
 if os.environ.get("BD_STREAM_OFF"):
     _lib.load().bd_linear_stream_set(0)
 model = BeaUTyDETR(text_encoder=None, cuda_graph=True, precision="fp16")
