@@ -167,29 +167,42 @@ linear_smallk_kernel(const float *__restrict__ A, int lda, const float *__restri
   for (int i = threadIdx.x; i < Np; i += blockDim.x) bs[i] = (bias && i < N) ? __ldg(bias + i) : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (long long r = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < M; r += static_cast<long long>(gridDim.x) * wpb) {
-    float x[8];
+  constexpr int RW = 4;  // rows per warp and pass: their input loads and output stores are in flight together
+  for (long long r0 = (static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5)) * RW; r0 < M;
+       r0 += static_cast<long long>(gridDim.x) * wpb * RW) {
+    float x[RW][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = k < K ? __ldg(A + r * lda + k) : 0.f;
+    for (int u = 0; u < RW; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[u][k] = (k < K && r0 + u < M) ? __ldg(A + (r0 + u) * lda + k) : 0.f;
     for (int n = 2 * lane; n < N; n += 64) {
-      float a0 = 0.f, a1 = 0.f;
+      float a0[RW], a1[RW];
+#pragma unroll
+      for (int u = 0; u < RW; ++u) a0[u] = a1[u] = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (k < K) {
           const float2 w = *reinterpret_cast<const float2 *>(Wt + k * Np + n);
-          a0 = fmaf(x[k], w.x, a0), a1 = fmaf(x[k], w.y, a1);
+#pragma unroll
+          for (int u = 0; u < RW; ++u) a0[u] = fmaf(x[u][k], w.x, a0[u]), a1[u] = fmaf(x[u][k], w.y, a1[u]);
         }
       }
-      a0 += bs[n], a1 += bs[n + 1];
-      if (relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
-      if (HALF) {
-        __half *y = static_cast<__half *>(Y) + r * ldy + n;
-        if (n + 1 < N) *reinterpret_cast<__half2 *>(y) = __floats2half2_rn(fminf(fmaxf(a0, -65504.f), 65504.f), fminf(fmaxf(a1, -65504.f), 65504.f));
-        else y[0] = __float2half_rn(fminf(fmaxf(a0, -65504.f), 65504.f));
-      } else {
-        float *y = static_cast<float *>(Y) + r * ldy + n;
-        if (n + 1 < N) *reinterpret_cast<float2 *>(y) = make_float2(a0, a1);
-        else y[0] = a0;
+      const float b0 = bs[n], b1 = bs[n + 1];
+#pragma unroll
+      for (int u = 0; u < RW; ++u) {
+        const long long r = r0 + u;
+        if (r >= M) break;
+        float v0 = a0[u] + b0, v1 = a1[u] + b1;
+        if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+        if (HALF) {
+          __half *y = static_cast<__half *>(Y) + r * ldy + n;
+          if (n + 1 < N) *reinterpret_cast<__half2 *>(y) = __floats2half2_rn(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
+          else y[0] = __float2half_rn(fminf(fmaxf(v0, -65504.f), 65504.f));
+        } else {
+          float *y = static_cast<float *>(Y) + r * ldy + n;
+          if (n + 1 < N) *reinterpret_cast<float2 *>(y) = make_float2(v0, v1);
+          else y[0] = v0;
+        }
       }
     }
   }
@@ -239,7 +252,7 @@ extern "C" int bd_linear_smallk(const float *A, int lda, const float *W, const f
              "bd_linear_smallk: needs 0 < K <= 8, N <= 4096, even ldy, 8-byte aligned Y, relu in {0, 1}");
   const int Np = (N + 1) & ~1;
   const size_t smem = sizeof(float) * static_cast<size_t>(K + 1) * Np;
-  const int blocks = bd::ceil_div(M, 8 * 16) < 4 * bd::sm_count() ? bd::ceil_div(M, 8 * 16) : 4 * bd::sm_count();
+  const int blocks = bd::ceil_div(M, 8 * 4 * 4) < 4 * bd::sm_count() ? bd::ceil_div(M, 8 * 4 * 4) : 4 * bd::sm_count();
   if (y_half)
     linear_smallk_kernel<true><<<blocks > 0 ? blocks : 1, 256, smem, bd::as_stream(stream)>>>(A, lda, W, bias, Y, ldy, M, N, K, relu);
   else
