@@ -792,6 +792,11 @@ __global__ void __launch_bounds__(TILES == 2 ? WS_THREADS : WS_THREADS1, (TILES 
 // be accumulated over the score columns: 128 TMEM columns, 53 KB of shared memory and <= 85 registers per thread,
 // i.e. FOUR CTAs per SM.  fp16 K / V rows by tensor copy as in the DIRECT variant (same column shift for odd
 // heads), same arithmetic: p = 2^(s - max), fp16 P, denominators from the ones tile.
+// Up to SH_EXTRA keys beyond the tile (Lk = 132 detected boxes: 4) are handled by the row's own thread on the
+// FMA pipe: their scores from the row's Q values (read back from the operand tile) and the fp16 K rows in global
+// memory (fp16 x fp16 products are exact in fp32, as on the tensor core), their probabilities rounded to fp16
+// like P, their share of P.V and of the denominator added to the accumulator columns read back from TMEM.
+constexpr int SH_EXTRA = 8;
 constexpr uint32_t SH_SMEM = 3 * QK_PART + 2 * ONES_BLK + 1024;  // Q | K | V | ones
 __global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -899,6 +904,39 @@ __global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const _
     tc::mbar_wait(tc::smem_u32(&bar_s), 0);
     tc::fence_after_sync();
     float mx = -INFINITY;
+    // ---- keys beyond the tile: scores on the FMA pipe (before this row's Q values are overwritten by P)
+    const int n_extra = max(0, p.Lk - WS_BK);
+    const int col0 = h * AT_HD - shift;  // global column of tile column 0 (a multiple of 8)
+    float s_x[SH_EXTRA], p_x[SH_EXTRA];
+#pragma unroll
+    for (int e = 0; e < SH_EXTRA; ++e) s_x[e] = -INFINITY, p_x[e] = 0.f;
+    if (n_extra > 0) {
+      uint4 qh[6];
+#pragma unroll
+      for (int ch = 0; ch < 6; ++ch) qh[ch] = *reinterpret_cast<const uint4 *>(sQ + tc::sw128_off(row, ch));
+      const __half *Kg = reinterpret_cast<const __half *>(p.K) + b * p.sk_b + col0;
+#pragma unroll
+      for (int e = 0; e < SH_EXTRA; ++e) {
+        if (e < n_extra && !(mask && mask[WS_BK + e])) {
+          const __half *kr = Kg + static_cast<long long>(WS_BK + e) * p.ldk;
+          float acc = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 6; ++ch) {
+            if (col0 + ch * 8 + 8 <= p.H * AT_HD) {  // inside the K rows (the Q values beyond are zero anyway)
+              const uint4 kv = __ldg(reinterpret_cast<const uint4 *>(kr + ch * 8));
+              const __half2 *q2 = reinterpret_cast<const __half2 *>(&qh[ch]), *k2 = reinterpret_cast<const __half2 *>(&kv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 qf = __half22float2(q2[i]), kf = __half22float2(k2[i]);
+                acc = fmaf(qf.x, kf.x, acc), acc = fmaf(qf.y, kf.y, acc);
+              }
+            }
+          }
+          s_x[e] = acc;
+          mx = fmaxf(mx, acc);
+        }
+      }
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       if (c < nch) {
@@ -912,6 +950,11 @@ __global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const _
     }
     const bool dead = mx == -INFINITY;  // every key masked
     const float neg_m = dead ? 0.f : -mx;
+    if (n_extra > 0) {
+#pragma unroll
+      for (int e = 0; e < SH_EXTRA; ++e)
+        if (s_x[e] != -INFINITY) p_x[e] = __half2float(__float2half_rn(tc::ex2_approx(s_x[e] + neg_m)));  // rounded like P
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       if (c < nch) {
@@ -949,11 +992,33 @@ __global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const _
         for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(a[i]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[32 + i] = __uint_as_float(c8[i]);
+        float l_run = __uint_as_float(l);
+        if (n_extra > 0) {  // the extra keys' share of P.V and of the denominator (tile column j = global column col0 + j)
+          const __half *Vg = reinterpret_cast<const __half *>(p.V) + b * p.sv_b + col0;
+#pragma unroll
+          for (int e = 0; e < SH_EXTRA; ++e) {
+            if (p_x[e] != 0.f) {
+              const __half *vr = Vg + static_cast<long long>(WS_BK + e) * p.ldv;
+              l_run += p_x[e];
+#pragma unroll
+              for (int ch = 0; ch < 5; ++ch) {
+                if (col0 + ch * 8 + 8 <= p.H * AT_HD) {
+                  const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(vr + ch * 8));
+                  const __half2 *v2 = reinterpret_cast<const __half2 *>(&vv);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 vf = __half22float2(v2[i]);
+                    o[ch * 8 + 2 * i] = fmaf(p_x[e], vf.x, o[ch * 8 + 2 * i]), o[ch * 8 + 2 * i + 1] = fmaf(p_x[e], vf.y, o[ch * 8 + 2 * i + 1]);
+                  }
+                }
+              }
+            }
+          }
+        }
         if (shift) {
 #pragma unroll
           for (int d = 0; d < AT_HD; ++d) o[d] = o[d + 4];
         }
-        const float l_run = __uint_as_float(l);
         const float inv = 1.0f / l_run;  // l == 0 (every key masked) -> NaN like the reference softmax
         const long long o_off = b * p.so_b + static_cast<long long>(q) * p.ldo + h * AT_HD;
 #pragma unroll
@@ -1147,7 +1212,7 @@ static int attention_tc_phases(const float *Q, int ldq, long long sq_b, const fl
         BD_REQUIRE(r == CUDA_SUCCESS, "bd_attention_tc: cuTensorMapEncodeTiled failed (%d) for B=%d Lk=%d ld=%d",
                    static_cast<int>(r), B, Lk, which ? ldv : ldk);
       }
-      if (hd == AT_HD && p.nk == 1 && g_attn_short)
+      if (hd == AT_HD && Lk <= WS_BK + SH_EXTRA && g_attn_short)
         BD_CUDA(bd::launch_pdl(attention_short_kernel, grid, dim3(WS_THREADS1), SH_SMEM, s, p), "bd_attention_tc");
       else if (hd == 64)
         BD_CUDA(bd::launch_pdl(attention_ws_kernel<1, 1, true, 64>, grid, dim3(WS_THREADS1), WS_SMEM_DIRECT, s, p), "bd_attention_tc");

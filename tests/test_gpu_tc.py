@@ -473,10 +473,12 @@ def test_persistent_linear_layernorm_equals_the_one_tile_kernel(cuda_lib, M, N, 
 
 
 @pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 1024, 80, True), (3, 256, 128, False), (2, 80, 80, True), (1, 300, 33, True),
-                                            (2, 130, 96, False), (1, 128, 1, False)])
+                                            (2, 130, 96, False), (1, 128, 1, False), (3, 256, 132, True), (2, 1024, 132, False),
+                                            (2, 200, 136, True), (1, 64, 129, True)])
 def test_attention_short_keys_kernel(cuda_lib, B, Lq, Lk, masked):
-    """Lk <= 128 with fp16 K / V: the four-CTAs-per-SM kernel (P in shared memory, O over the score columns) against
-    fp64 torch and against the general kernel (same arithmetic: equal up to the accumulation order of P.V)."""
+    """Lk <= 128 (+ up to 8 keys handled on the FMA pipe: Lk = 132 detected boxes) with fp16 K / V: the
+    four-CTAs-per-SM kernel (P in shared memory, O over the score columns) against fp64 torch and against the general
+    kernel (same arithmetic: equal up to the accumulation order)."""
     H, hd = 8, 36
     E = H * hd
     lib = cuda_lib.load()
