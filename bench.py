@@ -204,7 +204,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=296,
                     help="scenes per step per GPU (a multiple of 148 = whole waves of one furthest-point-sampling CTA per SM; "
-                         "measured on the final round-2 build: 5935 scenes/s at 148, 6105 at 296)")
+                         "measured on the final round-2 build: 6079 scenes/s at 148, 6260 at 296)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of CUDA-graph replay")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16x3"],
