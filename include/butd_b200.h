@@ -351,9 +351,10 @@ int bd_linear_stream_set(int on);
 int bd_linear_smallk(const float *A, int lda, const float *W, const float *bias, void *Y, int ldy,
                      int y_half, int M, int N, int K, int relu, bd_stream_t stream);
 
-/* Key sequences of at most 128 keys (one key tile) with fp16 K / V rows and head_dim 36 run a dedicated kernel: P
- * in shared memory, O over the score columns — 128 TMEM columns, four CTAs per SM (these launches are bound by the
- * per-CTA latency chain, not by arithmetic).  on = 0: the general kernel (A/B reference).  Default on. */
+/* Key sequences of at most 136 keys (one key tile of 128 + up to 8 keys handled on the FMA pipe: the 132 detected
+ * boxes) with fp16 K / V rows and head_dim 36 run a dedicated kernel: P in shared memory, O over the score columns
+ * — 128 TMEM columns, four CTAs per SM (these launches are bound by the per-CTA latency chain, not by arithmetic).
+ * on = 0: the general kernel (A/B reference).  Default on. */
 int bd_attention_tc_set_short(int on);
 
 /* RoBERTa input embeddings (text side, reference call site models/bdetr.py:168 -> transformers
