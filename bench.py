@@ -370,13 +370,24 @@ def main():
         peak, peak_src = measured_peaks()
         eng = model.engine()
         prof = _lib.Profiler()
-        for i in range(2):
-            eng.forward(dev_batch(i))
-        torch.cuda.synchronize()
-        with prof:
-            for i in range(min(K, 5)):
-                eng.forward(dev_batch(W + i))
-        torch.cuda.synchronize()
+        # every stream of the schedule is mapped onto the current one for this pass: each kernel then runs alone on
+        # the GPU, so its event time is its own (with the schedule's six streams the events of a side-stream kernel
+        # also contain the time it waits for SMs held by other streams' kernels); `share` = kernel time / sum
+        stream_names = ("side_stream", "text_stream", "kv_stream", "head_stream", "dec_stream", "aux_stream")
+        saved_streams = {n: getattr(eng, n) for n in stream_names}
+        for n in stream_names:
+            setattr(eng, n, torch.cuda.current_stream())
+        try:
+            for i in range(2):
+                eng.forward(dev_batch(i))
+            torch.cuda.synchronize()
+            with prof:
+                for i in range(min(K, 5)):
+                    eng.forward(dev_batch(W + i))
+            torch.cuda.synchronize()
+        finally:
+            for n, st in saved_streams.items():
+                setattr(eng, n, st)
         kernel_table = prof.table()
         rooflines = []
         for r in kernel_table:
