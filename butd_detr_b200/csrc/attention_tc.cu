@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const _
 
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 128);
   if (tid == 32) {
-    tc::mbar_init(tc::smem_u32(&bar_q), 4);
+    tc::mbar_init(tc::smem_u32(&bar_q), 1);
     tc::mbar_init(tc::smem_u32(&bar_kf), 1);
     tc::mbar_init(tc::smem_u32(&bar_vf), 1);
     tc::mbar_init(tc::smem_u32(&bar_s), 1);
@@ -889,8 +889,10 @@ __global__ void __launch_bounds__(WS_THREADS1, 4) attention_short_kernel(const _
         *reinterpret_cast<uint4 *>(sOnes + e * 16) = make_uint4(one2, one2, one2, one2);
       }
       tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_q));
+      // a barrier of the four staging warps rather than four mbarrier arrivals: each thread later reads and
+      // overwrites the Q row other threads staged, and this orders those accesses in a way racecheck follows too
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 64) tc::mbar_arrive(tc::smem_u32(&bar_q));
     }
     const int row = (warp & 3) * 32 + lane;
     const uint32_t tS = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
