@@ -279,7 +279,7 @@ struct BucketSmem {
 //   mbarrier -> REDUX pair over the posts.  Indices are written as raw keys and converted (an integer
 //   division) after the last round.
 template <int WARPS, int SLOTS, bool STATS = false>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1)
 fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ xyz, int ld, long long bstride, int N,
                   int m, int log2bs, int Q, float *__restrict__ tmin, int *__restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char bk_smem[];
@@ -617,7 +617,10 @@ cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, 
 }
 
 int g_force_cluster = -1;  // test hook: bd_fps_set_cluster()
-int g_bucket_warps = 16;   // tuning hook: bd_fps_grid_set_warps(); measured: 3.39 / 3.95 ms (16 warps) vs 4.00 / 4.48 ms (32) at 1 / 128 scenes
+// tuning hook: bd_fps_grid_set_warps(); 0 = by the number of scenes.  Measured (ms at 1 / 148 / 296 scenes): 16 warps, one
+// CTA per SM 3.35 / 4.13 / 8.18 (two waves); 32 warps 4.29 / 4.93 / 9.81; 8 warps, TWO CTAs per SM 4.82 / 6.07 / 7.21 —
+// a round of the 8-warp CTA is 1.75x as long, but two scenes share the SM and one's barrier waits hide under the other
+int g_bucket_warps = 0;
 int g_bucket_stats = 0;    // tools: bd_fps_grid_stats()
 
 constexpr int BUCKET_CAPACITY = 16 * 32 * 4 * 32;  // warps x lanes x slots x points per bucket = 65536 points
@@ -635,10 +638,10 @@ extern "C" int bd_fps_set_cluster(int cluster) {
   g_force_cluster = cluster;
   return BD_OK;
 }
-// Tuning hook: warps per CTA of the bucket kernel (16 or 32).
+// Tuning hook: warps per CTA of the bucket kernel (8, 16 or 32; 0 = chosen by the number of scenes).
 extern "C" int bd_fps_grid_set_warps(int warps) {
-  if (warps != 16 && warps != 32) {
-    bd::set_error("bd_fps_grid_set_warps: 16 or 32");
+  if (warps != 0 && warps != 8 && warps != 16 && warps != 32) {
+    bd::set_error("bd_fps_grid_set_warps: 0 (by the number of scenes), 8, 16 or 32");
     return BD_ERR_INVALID_ARG;
   }
   g_bucket_warps = warps;
@@ -675,12 +678,20 @@ extern "C" int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *
     cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_bucket_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_bucket_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_bucket_kernel<8, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BucketSmem)));
     return e;
   }), "bd_fps_grid");
+  int warps = g_bucket_warps;
+  if (warps == 0) {  // waves of one 16-warp CTA per SM (4.1 ms each) against waves of two 8-warp CTAs per SM (7.2 ms each)
+    const int n_sm = bd::sm_count();
+    warps = 4.1 * bd::ceil_div(B, n_sm) > 7.2 * bd::ceil_div(B, 2 * n_sm) ? 8 : 16;
+  }
   if (g_bucket_stats)
     fps_bucket_kernel<16, 4, true><<<B, 512, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
-  else if (g_bucket_warps == 32)
+  else if (warps == 32)
     fps_bucket_kernel<32, 2><<<B, 1024, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
+  else if (warps == 8)  // two scenes per SM
+    fps_bucket_kernel<8, 8><<<B, 256, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   else
     fps_bucket_kernel<16, 4><<<B, 512, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);
   BD_CHECK_LAUNCH("bd_fps_grid");

@@ -66,7 +66,7 @@ def _fps_grid(cuda_lib, xyz, m, radius, warps=16):
     try:
         cuda_lib.call("bd_fps_grid", xyz.data_ptr(), 3, B, N, m, ws.data_ptr(), scratch.data_ptr(), out.data_ptr())
     finally:
-        lib.bd_fps_grid_set_warps(16)
+        lib.bd_fps_grid_set_warps(0)
     return out
 
 
@@ -75,7 +75,7 @@ def _fps_grid(cuda_lib, xyz, m, radius, warps=16):
                                                ("uniform", 12, 30000, 512, -1.0), ("uniform", 2, 8192, 512, 0.05),
                                                ("room", 1, 65536, 300, 0.2), ("lattice", 2, 9001, 9001, 0.3),
                                                ("uniform", 2, 777, 300, -1.0)])
-@pytest.mark.parametrize("warps", [16, 32])
+@pytest.mark.parametrize("warps", [16, 32, 8])
 def test_fps_grid_bit_exact(cuda_lib, oracle_lib, kind, B, N, m, radius, warps):
     """bd_fps_grid (cell-list order, buckets of 32, bounding-box pruning) returns the oracle's indices bit
     for bit: ties on lattices, heavy duplication, more samples than distinct points, a partial last
@@ -102,6 +102,19 @@ def test_fps_benched_batch_sizes_bit_exact(cuda_lib, oracle_lib, ref_ext, ext, B
     assert torch.equal(ext.furthest_point_sampling(xd, m).cpu(), want), "drop-in furthest_point_sampling differs"
     if ref_ext is not None:
         assert torch.equal(ref_ext.furthest_point_sampling(xd, m).cpu(), want), "oracle differs from the reference kernel"
+
+
+def test_fps_grid_two_scenes_per_sm_at_the_bench_batch(cuda_lib, oracle_lib):
+    """296 scenes (bench.py's default batch): bd_fps_grid picks the 8-warp kernel, two CTAs per SM.  Same indices as
+    the 16-warp kernel on every scene, and as the C oracle on the first / last scenes of both halves."""
+    B, m = 296, 2048
+    xyz = cloud(900, 50000, "room", B)
+    xd = xyz.cuda()
+    auto = _fps_grid(cuda_lib, xd, m, 0.2, warps=0)
+    assert torch.equal(auto, _fps_grid(cuda_lib, xd, m, 0.2, warps=16))
+    assert torch.equal(auto, _fps_grid(cuda_lib, xd, m, 0.2, warps=8))
+    pick = [0, 147, 148, 295]
+    assert torch.equal(auto[pick].cpu(), oracle_lib.furthest_point_sampling(xyz[pick].contiguous(), m))
 
 
 def test_fps_grid_skipped_points_and_strided_rows(cuda_lib, oracle_lib):

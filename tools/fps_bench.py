@@ -1,5 +1,5 @@
 """FPS variants on 50k-point scenes: register-resident cluster kernel (bd_fps) vs the bucketed
-one-CTA-per-scene kernel over the cell list (bd_grid_build + bd_fps_grid, 16 / 32 warps).
+one-CTA-per-scene kernel over the cell list (bd_grid_build + bd_fps_grid, 8 / 16 / 32 warps).
 python tools/fps_bench.py [B ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,8 +24,8 @@ def bench(fn, n=5, warm=2):
     return e0.elapsed_time(e1) / n
 
 
-print("| B | bd_fps (cluster) ms | grid build ms | bd_fps_grid 16w ms | bd_fps_grid 32w ms | identical |")
-print("|---|---|---|---|---|---|")
+print("| B | bd_fps (cluster) ms | grid build ms | bd_fps_grid 16w ms | bd_fps_grid 32w ms | bd_fps_grid 8w x 2 CTAs/SM ms | identical |")
+print("|---|---|---|---|---|---|---|")
 for B in [int(a) for a in sys.argv[1:]] or [1, 4, 8, 16, 32, 64, 128, 148]:
     pcs = torch.from_numpy(np.stack([synth.synth_scene(50 + b)["point_clouds"] for b in range(B)])).cuda()
     a = torch.zeros(B, m, dtype=torch.int32, device="cuda")
@@ -36,13 +36,13 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 4, 8, 16, 32, 64, 128, 148]:
     tb = bench(lambda: _lib.call("bd_grid_build", pcs.data_ptr(), 6, B, N, 0.2, ws.data_ptr()))
     ts = []
     same = True
-    for w in (16, 32):
+    for w in (16, 32, 8):
         lib.bd_fps_grid_set_warps(w)
         b.zero_()
         ts.append(bench(lambda: _lib.call("bd_fps_grid", pcs.data_ptr(), 6, B, N, m, ws.data_ptr(), scratch.data_ptr(), b.data_ptr())))
         same = same and bool(torch.equal(a, b))
-    lib.bd_fps_grid_set_warps(16)
-    print(f"| {B} | {t0:.3f} | {tb:.3f} | {ts[0]:.3f} | {ts[1]:.3f} | {same} |", flush=True)
+    lib.bd_fps_grid_set_warps(0)
+    print(f"| {B} | {t0:.3f} | {tb:.3f} | {ts[0]:.3f} | {ts[1]:.3f} | {ts[2]:.3f} | {same} |", flush=True)
 
 # pruning statistics of the bucket kernel (counting variant)
 import ctypes
