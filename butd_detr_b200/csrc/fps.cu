@@ -435,12 +435,13 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
     // ---- the listed buckets, round-robin over the warps
     const int n = static_cast<int>(S.count[pp]);
     if (STATS && tid == 0) atomicAdd(&g_fps_stats[0], static_cast<unsigned long long>(n));
-    for (int e0 = warp; e0 < n; e0 += BK_U * WARPS) {
-      int bk[BK_U], si[BK_U];
-      float4 p[BK_U];
-      float told[BK_U];
+    constexpr int U = WARPS <= 8 ? 4 : BK_U;  // a round lists ~29 buckets: one batch per warp either way
+    for (int e0 = warp; e0 < n; e0 += U * WARPS) {
+      int bk[U], si[U];
+      float4 p[U];
+      float told[U];
 #pragma unroll
-      for (int u = 0; u < BK_U; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int e = e0 + u * WARPS;
         si[u] = e < n ? static_cast<int>(S.list[pp][e]) : -1;                          // state index
         bk[u] = e < n ? (si[u] / (32 * SLOTS)) * per + si[u] % (32 * SLOTS) : -1;     // bucket id (record order)
@@ -450,7 +451,7 @@ fps_bucket_kernel(const float4 *__restrict__ records, const float *__restrict__ 
       }
       if (STATS && lane == 0) atomicAdd(&g_fps_stats[1], 1ull);
 #pragma unroll
-      for (int u = 0; u < BK_U; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (bk[u] < 0) continue;  // warp-uniform
         const int i = (bk[u] << 5) + lane;
         const float d = bd::sqdist_ref(p[u].x, p[u].y, p[u].z, x1, y1, z1);
@@ -618,8 +619,8 @@ cudaError_t launch_resident(const float *xyz, int ld, long long bstride, int B, 
 
 int g_force_cluster = -1;  // test hook: bd_fps_set_cluster()
 // tuning hook: bd_fps_grid_set_warps(); 0 = by the number of scenes.  Measured (ms at 1 / 148 / 296 scenes): 16 warps, one
-// CTA per SM 3.35 / 4.13 / 8.18 (two waves); 32 warps 4.29 / 4.93 / 9.81; 8 warps, TWO CTAs per SM 4.82 / 6.07 / 7.21 —
-// a round of the 8-warp CTA is 1.75x as long, but two scenes share the SM and one's barrier waits hide under the other
+// CTA per SM 3.35 / 4.13 / 8.18 (two waves); 32 warps 4.29 / 4.93 / 9.81; 8 warps, TWO CTAs per SM 4.82 / 6.07 / 6.72 —
+// a round of the 8-warp CTA is 1.6x as long, but two scenes share the SM and one's barrier waits hide under the other
 int g_bucket_warps = 0;
 int g_bucket_stats = 0;    // tools: bd_fps_grid_stats()
 
@@ -682,9 +683,9 @@ extern "C" int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *
     return e;
   }), "bd_fps_grid");
   int warps = g_bucket_warps;
-  if (warps == 0) {  // waves of one 16-warp CTA per SM (4.1 ms each) against waves of two 8-warp CTAs per SM (7.2 ms each)
+  if (warps == 0) {  // waves of one 16-warp CTA per SM (4.1 ms each) against waves of two 8-warp CTAs per SM (6.7 ms each)
     const int n_sm = bd::sm_count();
-    warps = 4.1 * bd::ceil_div(B, n_sm) > 7.2 * bd::ceil_div(B, 2 * n_sm) ? 8 : 16;
+    warps = 4.1 * bd::ceil_div(B, n_sm) > 6.7 * bd::ceil_div(B, 2 * n_sm) ? 8 : 16;
   }
   if (g_bucket_stats)
     fps_bucket_kernel<16, 4, true><<<B, 512, sizeof(BucketSmem), stream>>>(records, xyz, ld, bstride, N, m, g.log2bs, g.Q, scratch, idx);

@@ -59,7 +59,7 @@ int bd_fps_resident_capacity(void);
  * cell-ordered points in buckets of 32 and skips every bucket whose bounding box is farther from
  * the new sample than the bucket's largest running distance (~2 % of the cloud is touched per
  * round), so a batch of up to 148 scenes runs in one wave; beyond one scene per SM an 8-warp variant puts two
- * scenes on each SM (296 scenes: 7.2 ms against two waves of 4.1 ms).  Same indices as bd_fps, bit for bit.
+ * scenes on each SM (296 scenes: 6.7 ms against two waves of 4.1 ms).  Same indices as bd_fps, bit for bit.
  * N <= bd_fps_grid_capacity(); `scratch`: bd_fps_grid_scratch_bytes(B, N) bytes. */
 int bd_fps_grid(const float *xyz, int ld, int B, int N, int m, void *grid_workspace, float *scratch,
                 int *idx, bd_stream_t stream);
