@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 def pytest_runtest_logreport(report):
     """Failures are also appended to gpurun_out/test_failures.log: that directory comes back from a GPU box even when
-    only the tail of the terminal output does (one of nine full runs of the GPU suite on fresh boxes stopped at a
+    only the tail of the terminal output does (one full run of the GPU suite on a fresh box stopped at a
     failure whose text was lost and which did not repeat — DESIGN.md section 9)."""
     if report.failed:
         try:
