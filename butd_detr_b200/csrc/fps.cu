@@ -636,6 +636,10 @@ extern "C" long long bd_fps_grid_scratch_bytes(int B, int N) {
 
 // Test / tuning hook: force the cluster size used for large clouds (4, 8 or 16; -1 = automatic).
 extern "C" int bd_fps_set_cluster(int cluster) {
+  if (cluster != -1 && cluster != 4 && cluster != 8 && cluster != 16) {
+    bd::set_error("bd_fps_set_cluster: -1 (automatic), 4, 8 or 16");
+    return BD_ERR_INVALID_ARG;
+  }
   g_force_cluster = cluster;
   return BD_OK;
 }

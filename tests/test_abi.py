@@ -44,6 +44,18 @@ def test_invalid_arguments_return_error_codes_not_exit():
     assert lib.bd_linear_f32(None, 0, None, 0, None, None, None, 0, 1, 1, 1, 0, None) == 1
 
 
+def test_tuning_hooks_validate_their_argument():
+    """Host-only switches: bad values are refused with an error code, good ones accepted (and restored)."""
+    from butd_detr_b200 import _lib
+    lib = _lib.load()
+    for w in (8, 16, 32, 0):  # 8 = two CTAs per SM, 0 = chosen by the number of scenes (default, restored last)
+        assert lib.bd_fps_grid_set_warps(w) == 0
+    assert lib.bd_fps_grid_set_warps(12) == 1
+    assert b"bd_fps_grid_set_warps" in lib.bd_last_error()
+    assert lib.bd_fps_set_cluster(5) == 1
+    assert lib.bd_fps_set_cluster(-1) == 0
+
+
 def test_sass_uses_cluster_and_async_instructions():
     """The FPS kernel must really be the cluster/DSMEM design (st.async + mbarrier)."""
     import subprocess
